@@ -1,0 +1,471 @@
+// clahe.cu - cv::CLAHE::apply (8-bit) and the aclahe HSV frame wrapper for sm_100a.
+//   reference call sites: modules/aclahe/src/aclahe.cpp:152-154 (BGR2HSV, split), :175-187 (apply),
+//   modules/aclahe/python/functions.py:24-27, modules/aclahe/python/main.py:19-20.
+//   The arithmetic itself is OpenCV's (not vendored in the reference); it is restated from SURVEY
+//   appendix A.2 and pinned bit-exact against cv2 4.13.0 by tests/.
+// Three passes: (1) per-tile histograms with per-warp privatised shared-memory atomics,
+// (2) clip + redistribute + block prefix scan -> per-tile LUT, (3) bilinear blend of four tile LUTs,
+// fused with the BGR<->HSV conversions (and, in the chain, with the histretch LUT in front and the
+// dehaze min/max reduction behind).
+#include "common.cuh"
+
+constexpr int TH_THREADS = 256;
+constexpr int TH_WARPS = TH_THREADS / 32;
+
+struct TileGeom {
+  int W, H;      // image
+  int EW, EH;    // extended (padded) size used for LUT building
+  int tx, ty;    // grid
+  int tw, th;    // tile size
+};
+
+static TileGeom make_geom(int W, int H, int tx, int ty) {
+  TileGeom g;
+  g.W = W; g.H = H; g.tx = tx; g.ty = ty;
+  if (W % tx == 0 && H % ty == 0) {
+    g.EW = W; g.EH = H;
+  } else {  // OpenCV pads both dimensions (a full extra tile count when one of them divides evenly)
+    g.EW = W + tx - W % tx;
+    g.EH = H + ty - H % ty;
+  }
+  g.tw = g.EW / tx;
+  g.th = g.EH / ty;
+  return g;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// ---- pass 1: per-tile histograms ---------------------------------------------------------------
+// FRAME=false: src is an 8U plane.  FRAME=true: src is bgr8 and the value is the HSV V channel
+// (max(b,g,r)), optionally pushed through two 256-entry LUTs (trunc / rint flavour chosen by x) =
+// the histretch stretch followed by the HSV->BGR->HSV round trip of its V channel.
+template <bool FRAME>
+__global__ void __launch_bounds__(TH_THREADS) tilehist_kernel(const uint8_t* __restrict__ src, TileGeom g, int splits,
+                                                              const uint8_t* __restrict__ prelut2 /*[n][2][256] or null*/,
+                                                              int body_w, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[TH_WARPS][256];
+  __shared__ uint8_t s_pre[2][256];
+  int f = blockIdx.z;
+  for (int i = threadIdx.x; i < TH_WARPS * 256; i += TH_THREADS) (&sh[0][0])[i] = 0;
+  if (FRAME) {
+    s_pre[0][threadIdx.x] = prelut2 ? prelut2[((size_t)f * 2 + 0) * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
+    s_pre[1][threadIdx.x] = prelut2 ? prelut2[((size_t)f * 2 + 1) * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
+  }
+  __syncthreads();
+  int tile = blockIdx.x;
+  int tyi = tile / g.tx, txi = tile % g.tx;
+  int rows_per = (g.th + splits - 1) / splits;
+  int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, g.th);
+  uint32_t* myh = sh[threadIdx.x >> 5];
+  size_t n_px = (size_t)g.W * g.H;
+  const uint8_t* base = src + (size_t)f * n_px * (FRAME ? 3 : 1);
+  int x_begin = txi * g.tw, y_begin = tyi * g.th;
+  bool vec = (g.EW == g.W) && (g.EH == g.H) && (g.tw % 16 == 0) && ((((uintptr_t)base) & 15) == 0);
+  if (vec) {
+    int gpr = g.tw / 16;  // 16-pixel groups per tile row
+    int total = (r1 - r0) * gpr;
+    for (int i = threadIdx.x; i < total; i += TH_THREADS) {
+      int ry = i / gpr, gx = i - ry * gpr;
+      int y = y_begin + r0 + ry, x = x_begin + gx * 16;
+      if (FRAME) {
+        const uint4* q = reinterpret_cast<const uint4*>(base + ((size_t)y * g.W + x) * 3);
+        uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          int i0 = 3 * k, i1 = 3 * k + 1, i2 = 3 * k + 2;
+          int bb = (w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xff;
+          int gg = (w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xff;
+          int rr = (w[i2 >> 2] >> ((i2 & 3) * 8)) & 0xff;
+          int v = imax3(bb, gg, rr);
+          v = s_pre[(x + k) < body_w ? 0 : 1][v];
+          atomicAdd(&myh[v], 1u);
+        }
+      } else {
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(base + (size_t)y * g.W + x));
+        uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          atomicAdd(&myh[w[k] & 0xff], 1u);
+          atomicAdd(&myh[(w[k] >> 8) & 0xff], 1u);
+          atomicAdd(&myh[(w[k] >> 16) & 0xff], 1u);
+          atomicAdd(&myh[w[k] >> 24], 1u);
+        }
+      }
+    }
+  } else {
+    int total = (r1 - r0) * g.tw;
+    for (int i = threadIdx.x; i < total; i += TH_THREADS) {
+      int ry = i / g.tw, rx = i - ry * g.tw;
+      int y = reflect101(y_begin + r0 + ry, g.H), x = reflect101(x_begin + rx, g.W);
+      int v;
+      if (FRAME) {
+        const uint8_t* p = base + ((size_t)y * g.W + x) * 3;
+        v = imax3(p[0], p[1], p[2]);
+        v = s_pre[x < body_w ? 0 : 1][v];
+      } else {
+        v = base[(size_t)y * g.W + x];
+      }
+      atomicAdd(&myh[v], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t s = 0;
+#pragma unroll
+  for (int w = 0; w < TH_WARPS; w++) s += sh[w][threadIdx.x];
+  if (s) atomicAdd(&hist[((size_t)f * g.tx * g.ty + tile) * 256 + threadIdx.x], s);
+}
+
+// ---- pass 2: clip, redistribute, scan, LUT -------------------------------------------------------
+__device__ __forceinline__ uint32_t block_incl_scan_256(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+  int t = threadIdx.x;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= d) incl += o;
+  }
+  __syncthreads();  // protect s_warp reuse
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  total = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t x = s_warp[k];
+    if (k < (t >> 5)) base += x;
+    total += x;
+  }
+  return incl + base;
+}
+
+// one block per (tile, frame); `cl` = clip limit in counts (0: no clipping); n_cl > 1 builds LUTs for
+// several clip limits at once (entropy sweep): lut layout [frame][tile][icl][256]
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint32_t* __restrict__ hist, const int* __restrict__ cls, int n_cl,
+                                                        float lut_scale, uint8_t* __restrict__ lut) {
+  __shared__ uint32_t s_warp[8];
+  int t = threadIdx.x;
+  size_t tile = blockIdx.x;
+  uint32_t h0 = hist[tile * 256 + t];
+  for (int ic = 0; ic < n_cl; ic++) {
+    int cl = cls[ic];
+    uint32_t h = h0;
+    if (cl > 0) {
+      uint32_t excess = h > (uint32_t)cl ? h - cl : 0, clipped;
+      block_incl_scan_256(excess, s_warp, clipped);
+      h = min(h, (uint32_t)cl);
+      uint32_t batch = clipped / 256, resid = clipped - batch * 256;
+      h += batch;
+      if (resid) {
+        uint32_t step = max(256u / resid, 1u);
+        if (t % step == 0 && t / step < resid) h++;
+      }
+    }
+    uint32_t tot;
+    uint32_t cum = block_incl_scan_256(h, s_warp, tot);
+    lut[(tile * n_cl + ic) * 256 + t] = (uint8_t)sat_rint_u8(__fmul_rn((float)cum, lut_scale));
+  }
+}
+
+// ---- pass 3: bilinear LUT interpolation ---------------------------------------------------------
+struct Interp {
+  int t1, t2;
+  float a, a1;
+};
+__device__ __forceinline__ Interp interp_coord(int x, float inv_t, int ntile) {
+  float f = __fsub_rn(__fmul_rn((float)x, inv_t), 0.5f);
+  int t1 = (int)floorf(f);
+  Interp r;
+  r.a = __fsub_rn(f, (float)t1);
+  r.a1 = __fsub_rn(1.0f, r.a);
+  r.t2 = min(t1 + 1, ntile - 1);
+  r.t1 = max(t1, 0);
+  return r;
+}
+__device__ __forceinline__ int clahe_blend(float l11, float l12, float l21, float l22, const Interp& ix, const Interp& iy) {
+  float top = __fadd_rn(__fmul_rn(l11, ix.a1), __fmul_rn(l12, ix.a));
+  float bot = __fadd_rn(__fmul_rn(l21, ix.a1), __fmul_rn(l22, ix.a));
+  float res = __fadd_rn(__fmul_rn(top, iy.a1), __fmul_rn(bot, iy.a));
+  return sat_rint_u8(res);
+}
+
+constexpr int AP_THREADS = 256;
+
+// Processes `rows_per` image rows per block.  MODE 0: plane in / plane out.  MODE 1: bgr8 frame:
+// [optional stretch LUT on V + HSV->BGR->HSV round trip] -> CLAHE on V -> HSV->BGR, and optional
+// joint min/max of the output bytes into FrameState (dehaze D0, bgdehaze/main.py:17).
+template <int MODE>
+__global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                 TileGeom g, int rows_per, const uint8_t* __restrict__ lut,
+                                                                 const uint8_t* __restrict__ prelut /*[n][256] or null*/,
+                                                                 int body_w, FrameState* fs) {
+  extern __shared__ uint8_t s_lut[];  // [3][tx][256] when it fits
+  __shared__ uint8_t s_pre[256];
+  __shared__ int s_sdiv[256], s_hdiv[256];
+  int f = blockIdx.y;
+  int y0 = blockIdx.x * rows_per, y1 = min(y0 + rows_per, g.H);
+  float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
+  const uint8_t* flut = lut + (size_t)f * g.tx * g.ty * 256;
+  // tile rows needed by this band
+  int ty_lo = interp_coord(y0, inv_th, g.ty).t1;
+  int ty_hi = interp_coord(y1 - 1, inv_th, g.ty).t2;
+  bool staged = (ty_hi - ty_lo + 1) <= 3 && g.tx <= 32;
+  if (staged) {
+    int nbytes = (ty_hi - ty_lo + 1) * g.tx * 256;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(flut + (size_t)ty_lo * g.tx * 256);
+    for (int i = threadIdx.x; i < nbytes / 4; i += AP_THREADS) reinterpret_cast<uint32_t*>(s_lut)[i] = __ldg(s4 + i);
+  }
+  if (MODE == 1) {
+    s_pre[threadIdx.x] = prelut ? prelut[(size_t)f * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
+    s_sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
+    s_hdiv[threadIdx.x] = hsv_hdiv(threadIdx.x);
+  }
+  __syncthreads();
+  const uint8_t* L = staged ? s_lut : flut;
+  int ty_off = staged ? ty_lo : 0;
+  size_t n_px = (size_t)g.W * g.H;
+  const uint8_t* in = src + (size_t)f * n_px * (MODE ? 3 : 1);
+  uint8_t* out = dst + (size_t)f * n_px * (MODE ? 3 : 1);
+  unsigned int mn = 255, mx = 0;
+  const bool has_pre = (prelut != nullptr);
+
+  auto lookup = [&](int v, const Interp& ix, const Interp& iy) {
+    const uint8_t* r1 = L + (size_t)(iy.t1 - ty_off) * g.tx * 256;
+    const uint8_t* r2 = L + (size_t)(iy.t2 - ty_off) * g.tx * 256;
+    float l11 = (float)r1[ix.t1 * 256 + v], l12 = (float)r1[ix.t2 * 256 + v];
+    float l21 = (float)r2[ix.t1 * 256 + v], l22 = (float)r2[ix.t2 * 256 + v];
+    return clahe_blend(l11, l12, l21, l22, ix, iy);
+  };
+  auto do_pixel = [&](int& b, int& gg, int& r, int x, const Interp& iy) {
+    bool tr = x < body_w;
+    int h, s, v;
+    if (has_pre) {  // histretch on V (intended order) fused in front, incl. its colour round trip
+      bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
+      hsv2bgr_u8(h, s, s_pre[v], tr, b, gg, r);
+    }
+    bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
+    Interp ix = interp_coord(x, inv_tw, g.tx);
+    v = lookup(v, ix, iy);
+    hsv2bgr_u8(h, s, v, tr, b, gg, r);
+    mn = min(mn, (unsigned)imin3(b, gg, r));
+    mx = max(mx, (unsigned)imax3(b, gg, r));
+  };
+
+  bool vec = (g.W % 16 == 0) && (((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0);
+  if (vec) {
+    int gpr = g.W / 16;
+    int total = (y1 - y0) * gpr;
+    for (int i = threadIdx.x; i < total; i += AP_THREADS) {
+      int ry = i / gpr, gx = i - ry * gpr;
+      int y = y0 + ry, x = gx * 16;
+      Interp iy = interp_coord(y, inv_th, g.ty);
+      if (MODE == 0) {
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(in + (size_t)y * g.W + x));
+        uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          int v = (w[k >> 2] >> ((k & 3) * 8)) & 0xff;
+          Interp ix = interp_coord(x + k, inv_tw, g.tx);
+          int o = lookup(v, ix, iy);
+          w[k >> 2] = (w[k >> 2] & ~(0xffu << ((k & 3) * 8))) | ((uint32_t)o << ((k & 3) * 8));
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)y * g.W + x) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        const uint4* q = reinterpret_cast<const uint4*>(in + ((size_t)y * g.W + x) * 3);
+        uint4 a = __ldg(q), bq = __ldg(q + 1), c = __ldg(q + 2);
+        uint32_t w[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          int i0 = 3 * k, i1 = 3 * k + 1, i2 = 3 * k + 2;
+          int b = (w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xff;
+          int gg = (w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xff;
+          int r = (w[i2 >> 2] >> ((i2 & 3) * 8)) & 0xff;
+          do_pixel(b, gg, r, x + k, iy);
+          w[i0 >> 2] = (w[i0 >> 2] & ~(0xffu << ((i0 & 3) * 8))) | ((uint32_t)b << ((i0 & 3) * 8));
+          w[i1 >> 2] = (w[i1 >> 2] & ~(0xffu << ((i1 & 3) * 8))) | ((uint32_t)gg << ((i1 & 3) * 8));
+          w[i2 >> 2] = (w[i2 >> 2] & ~(0xffu << ((i2 & 3) * 8))) | ((uint32_t)r << ((i2 & 3) * 8));
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + ((size_t)y * g.W + x) * 3);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+      }
+    }
+  } else {
+    int total = (y1 - y0) * g.W;
+    for (int i = threadIdx.x; i < total; i += AP_THREADS) {
+      int ry = i / g.W, x = i - ry * g.W;
+      int y = y0 + ry;
+      Interp iy = interp_coord(y, inv_th, g.ty);
+      if (MODE == 0) {
+        Interp ix = interp_coord(x, inv_tw, g.tx);
+        out[(size_t)y * g.W + x] = (uint8_t)lookup(in[(size_t)y * g.W + x], ix, iy);
+      } else {
+        const uint8_t* p = in + ((size_t)y * g.W + x) * 3;
+        int b = p[0], gg = p[1], r = p[2];
+        do_pixel(b, gg, r, x, iy);
+        uint8_t* o = out + ((size_t)y * g.W + x) * 3;
+        o[0] = (uint8_t)b; o[1] = (uint8_t)gg; o[2] = (uint8_t)r;
+      }
+    }
+  }
+  if (MODE == 1 && fs) {
+    mn = warp_reduce_min_u32(mn);
+    mx = warp_reduce_max_u32(mx);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&fs[f].kmin, mn);
+      atomicMax(&fs[f].kmax, mx);
+    }
+  }
+}
+
+// composite LUTs for pass 1 of the fused histretch->aclahe head: V after stretch and after the
+// HSV->BGR->HSV round trip, for the truncating body and the rounding tail of a row.
+__global__ void prelut2_kernel(const uint8_t* __restrict__ lut1, uint8_t* __restrict__ lut2) {
+  int f = blockIdx.x, t = threadIdx.x;
+  int v = lut1[(size_t)f * 256 + t];
+  lut2[((size_t)f * 2 + 0) * 256 + t] = (uint8_t)hsv_roundtrip_v(v, true);
+  lut2[((size_t)f * 2 + 1) * 256 + t] = (uint8_t)hsv_roundtrip_v(v, false);
+}
+
+// ---- host-side drivers (device pointers) ----------------------------------------------------------
+static int body_width(int w, int hsv_round) {
+  if (hsv_round == UWIP_HSV_ROUND_TRUNC) return w;
+  if (hsv_round == UWIP_HSV_ROUND_RINT) return 0;
+  return 32 * (w / 32);
+}
+
+static int clip_count(double clip, int area) {
+  if (!(clip > 0)) return 0;
+  int cl = (int)(clip * area / 256.0);
+  return cl < 1 ? 1 : cl;
+}
+
+static int pick_splits(uwip_ctx* ctx, const TileGeom& g, int n) {
+  int tiles = g.tx * g.ty * n;
+  int want = ctx->sm_count * 4;  // ~4 blocks per SM
+  int s = (want + tiles - 1) / tiles;
+  int max_s = (g.th + 7) / 8;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+static int clahe_common(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty,
+                        bool frame, int hsv_round, const uint8_t* d_prelut, FrameState* fs) {
+  UWIP_REQUIRE(ctx, tx >= 1 && ty >= 1 && tx <= 256 && ty <= 256, "tile grid out of range");
+  UWIP_REQUIRE(ctx, w >= 1 && h >= 1 && n >= 1, "bad size");
+  TileGeom g = make_geom(w, h, tx, ty);
+  UWIP_REQUIRE(ctx, (g.EW == w || 2 * w - 2 >= g.EW - 1 || w == 1) && (g.EH == h || 2 * h - 2 >= g.EH - 1 || h == 1),
+               "image too small for this tile grid (reflect-101 padding undefined)");
+  size_t ntile = (size_t)n * tx * ty;
+  uint32_t* d_th = (uint32_t*)uwip_slot(ctx, SLOT_TILEHIST, ntile * 256 * 4);
+  uint8_t* d_tl = (uint8_t*)uwip_slot(ctx, SLOT_TILELUT, ntile * 256 + 16);
+  int* d_cl = (int*)uwip_slot(ctx, SLOT_MISC, 256);
+  if (!d_th || !d_tl || !d_cl) return UWIP_ERR_NOMEM;
+  uint8_t* d_pre2 = nullptr;
+  int bw = body_width(w, hsv_round);
+  if (d_prelut) {
+    d_pre2 = (uint8_t*)uwip_slot(ctx, SLOT_LUT, (size_t)n * 256 * 4) + (size_t)n * 256;  // second half of the LUT slot
+    UWIP_LAUNCH(ctx, "prelut2", prelut2_kernel, n, 256, 0, d_prelut, d_pre2);
+  }
+  UWIP_CUDA(ctx, cudaMemsetAsync(d_th, 0, ntile * 256 * 4, ctx->stream));
+  int splits = pick_splits(ctx, g, n);
+  dim3 grid1(tx * ty, splits, n);
+  if (frame)
+    UWIP_LAUNCH(ctx, "clahe_tilehist", tilehist_kernel<true>, grid1, TH_THREADS, 0, d_src, g, splits, d_pre2, bw, d_th);
+  else
+    UWIP_LAUNCH(ctx, "clahe_tilehist", tilehist_kernel<false>, grid1, TH_THREADS, 0, d_src, g, splits, (const uint8_t*)nullptr, bw, d_th);
+  int cl = clip_count(clip, g.tw * g.th);
+  UWIP_CUDA(ctx, cudaMemcpyAsync(d_cl, &cl, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  float lut_scale = 255.0f / (float)(g.tw * g.th);
+  UWIP_LAUNCH(ctx, "clahe_lut", clahe_lut_kernel, (unsigned)ntile, 256, 0, d_th, d_cl, 1, lut_scale, d_tl);
+  int rows_per = 8;
+  while (rows_per > 1 && (long long)cdiv(h, rows_per) * n < (long long)ctx->sm_count * 4) rows_per /= 2;
+  dim3 grid3(cdiv(h, rows_per), n);
+  size_t smem = (size_t)3 * (tx <= 32 ? tx : 0) * 256;
+  if (frame)
+    UWIP_LAUNCH(ctx, "clahe_apply", clahe_apply_kernel<1>, grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl, d_prelut, bw, fs);
+  else
+    UWIP_LAUNCH(ctx, "clahe_apply", clahe_apply_kernel<0>, grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl,
+                (const uint8_t*)nullptr, bw, (FrameState*)nullptr);
+  return UWIP_OK;
+}
+
+int clahe_planes_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty) {
+  return clahe_common(ctx, d_src, d_dst, n, w, h, clip, tx, ty, false, 0, nullptr, nullptr);
+}
+
+int aclahe_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty,
+                      int hsv_round, const uint8_t* d_prelut, FrameState* fs) {
+  return clahe_common(ctx, d_src, d_dst, n, w, h, clip, tx, ty, true, hsv_round, d_prelut, fs);
+}
+
+// ---- entropy sweep over clip limits for one grid -----------------------------------
+// Tile histograms do not depend on the clip limit: build them once, derive one LUT set per clip
+// limit, then ONE pixel pass accumulates the histogram of every CLAHE output without writing images.
+constexpr int SW_MAX_CL = 64;
+__global__ void __launch_bounds__(256) sweep_hist_kernel(const uint8_t* __restrict__ src, TileGeom g, int rows_per,
+                                                         const uint8_t* __restrict__ lut /*[tile][n_cl][256]*/, int n_cl,
+                                                         uint32_t* __restrict__ out_hist /*[n_cl][256]*/) {
+  extern __shared__ uint32_t s_hist[];  // [n_cl][256]
+  for (int i = threadIdx.x; i < n_cl * 256; i += 256) s_hist[i] = 0;
+  __syncthreads();
+  int y0 = blockIdx.x * rows_per, y1 = min(y0 + rows_per, g.H);
+  float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
+  int total = (y1 - y0) * g.W;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    int ry = i / g.W, x = i - ry * g.W, y = y0 + ry;
+    Interp iy = interp_coord(y, inv_th, g.ty), ix = interp_coord(x, inv_tw, g.tx);
+    int v = src[(size_t)y * g.W + x];
+    const uint8_t* p11 = lut + ((size_t)(iy.t1 * g.tx + ix.t1) * n_cl) * 256 + v;
+    const uint8_t* p12 = lut + ((size_t)(iy.t1 * g.tx + ix.t2) * n_cl) * 256 + v;
+    const uint8_t* p21 = lut + ((size_t)(iy.t2 * g.tx + ix.t1) * n_cl) * 256 + v;
+    const uint8_t* p22 = lut + ((size_t)(iy.t2 * g.tx + ix.t2) * n_cl) * 256 + v;
+    for (int c = 0; c < n_cl; c++) {
+      int o = clahe_blend((float)__ldg(p11 + c * 256), (float)__ldg(p12 + c * 256), (float)__ldg(p21 + c * 256),
+                          (float)__ldg(p22 + c * 256), ix, iy);
+      atomicAdd(&s_hist[c * 256 + o], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_cl * 256; i += 256)
+    if (s_hist[i]) atomicAdd(&out_hist[i], s_hist[i]);
+}
+
+int clahe_entropy_sweep_dev(uwip_ctx* ctx, const uint8_t* d_plane, int w, int h, int tiles, const double* clips, int n_clips,
+                            int flavour, float* entropies_host) {
+  UWIP_REQUIRE(ctx, n_clips >= 1 && n_clips <= SW_MAX_CL, "1..64 clip limits per sweep");
+  UWIP_REQUIRE(ctx, tiles >= 1 && tiles <= 256, "tile grid out of range");
+  TileGeom g = make_geom(w, h, tiles, tiles);
+  UWIP_REQUIRE(ctx, (g.EW == w || 2 * w - 2 >= g.EW - 1) && (g.EH == h || 2 * h - 2 >= g.EH - 1), "image too small for grid");
+  size_t ntile = (size_t)tiles * tiles;
+  uint32_t* d_th = (uint32_t*)uwip_slot(ctx, SLOT_TILEHIST, ntile * 256 * 4);
+  uint8_t* d_tl = (uint8_t*)uwip_slot(ctx, SLOT_TILELUT, ntile * 256 * n_clips + 16);
+  char* d_sw = (char*)uwip_slot(ctx, SLOT_SWEEP, 1024 + (size_t)n_clips * 256 * 4 + (size_t)n_clips * 4);
+  if (!d_th || !d_tl || !d_sw) return UWIP_ERR_NOMEM;
+  int* d_cl = (int*)d_sw;
+  uint32_t* d_oh = (uint32_t*)(d_sw + 1024);
+  float* d_ent = (float*)(d_sw + 1024 + (size_t)n_clips * 256 * 4);
+  int cls[SW_MAX_CL];
+  for (int i = 0; i < n_clips; i++) cls[i] = clip_count(clips[i], g.tw * g.th);
+  UWIP_CUDA(ctx, cudaMemcpyAsync(d_cl, cls, sizeof(int) * n_clips, cudaMemcpyHostToDevice, ctx->stream));
+  UWIP_CUDA(ctx, cudaMemsetAsync(d_th, 0, ntile * 256 * 4, ctx->stream));
+  UWIP_CUDA(ctx, cudaMemsetAsync(d_oh, 0, (size_t)n_clips * 256 * 4, ctx->stream));
+  int splits = pick_splits(ctx, g, 1);
+  dim3 grid1(tiles * tiles, splits, 1);
+  UWIP_LAUNCH(ctx, "clahe_tilehist", tilehist_kernel<false>, grid1, TH_THREADS, 0, d_plane, g, splits, (const uint8_t*)nullptr, 0, d_th);
+  float lut_scale = 255.0f / (float)(g.tw * g.th);
+  UWIP_LAUNCH(ctx, "clahe_lut", clahe_lut_kernel, (unsigned)ntile, 256, 0, d_th, d_cl, n_clips, lut_scale, d_tl);
+  int rows_per = 4;
+  size_t smem = (size_t)n_clips * 256 * 4;
+  UWIP_CUDA(ctx, cudaFuncSetAttribute(sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  UWIP_LAUNCH(ctx, "clahe_sweep_hist", sweep_hist_kernel, cdiv(h, rows_per), 256, smem, d_plane, g, rows_per, d_tl, n_clips, d_oh);
+  UWIP_CHECK(k_entropy(ctx, d_oh, n_clips, w, h, flavour, d_ent));
+  UWIP_CUDA(ctx, cudaMemcpyAsync(entropies_host, d_ent, sizeof(float) * n_clips, cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UWIP_OK;
+}
