@@ -110,7 +110,8 @@ struct FrameState {
   unsigned int kmin, kmax;     // atomicMin / atomicMax targets
   // dehaze D1: arg-min results (first flat index) and background light
   unsigned int idx0, idx1;
-  double B[3];
+  double B[3];                 // Background_light(normI, w)  (used by dehazed_BG, BGDehaze.py:51)
+  double Bt[3];                // Background_light(normI, 15) (used inside transmission_map, :30,52)
   // dehaze D6: per-channel J min / max (ordered-uint encoding of the double) and fixed-point sums
   unsigned long long jmin_key[2], jmax_key[2];
   long long jsum_fix[2];       // sum of J * 2^32 (deterministic integer accumulation)

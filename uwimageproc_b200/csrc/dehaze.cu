@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __res
 
 // finish the arg-min and form the background light B = mean of the two selected pixels (BGDehaze.py:22-26)
 __global__ void __launch_bounds__(256) bglight_finish_kernel(const uint8_t* __restrict__ src, int W, int H,
-                                                             const ArgPartial* __restrict__ partials, int n_part, FrameState* fs) {
+                                                             const ArgPartial* __restrict__ partials, int n_part, FrameState* fs,
+                                                             int write_B, int write_Bt) {
   __shared__ ArgPartial s_part[8];
   int f = blockIdx.x;
   const ArgPartial* pp = partials + (size_t)f * n_part;
@@ -218,12 +219,14 @@ __global__ void __launch_bounds__(256) bglight_finish_kernel(const uint8_t* __re
       a.i0 = a.i1 = 0;
       s.nan_flag = 1;
     }
-    s.idx0 = a.i0; s.idx1 = a.i1;
+    if (write_B) { s.idx0 = a.i0; s.idx1 = a.i1; }
     const uint8_t* img = src + (size_t)f * W * H * 3;
     for (int c = 0; c < 3; c++) {
       double v0 = (double)((int)img[(size_t)a.i0 * 3 + c] - kmin) / range;
       double v1 = (double)((int)img[(size_t)a.i1 * 3 + c] - kmin) / range;
-      s.B[c] = (v0 + v1) / 2.0;
+      double b = (v0 + v1) / 2.0;
+      if (write_B) s.B[c] = b;
+      if (write_Bt) s.Bt[c] = b;
     }
   }
 }
@@ -241,7 +244,7 @@ __global__ void traw_kernel(const uint8_t* __restrict__ mplanes, int W, int H, c
   size_t pix = (size_t)y * W + x;
   for (int c = 0; c < 2; c++) {
     int m = touches ? 0 : (int)mplanes[(size_t)c * W * H + pix] - kmin;
-    t_raw[(size_t)c * W * H + pix] = 1.0 - ((double)m / range) / s.B[c];
+    t_raw[(size_t)c * W * H + pix] = 1.0 - ((double)m / range) / s.Bt[c];
   }
 }
 
@@ -302,7 +305,7 @@ struct GfCommon {
 // ---- shared per-CTA frame constants --------------------------------------------------------------
 struct FrameConst {
   int kmin, range;
-  double B[3];
+  double B[3], Bt[3];
   // restored-image parameters (valid after GF1b): J min / 1/(max-min), red LUT scalars
   double jmin[2], jinv[2];
   int yi_min, yi_rng, yj_min, yj_rng;
@@ -312,6 +315,7 @@ __device__ __forceinline__ void load_frame_const(const FrameState& s, FrameConst
   c.kmin = s.kmin;
   c.range = (int)s.kmax - (int)s.kmin;
   c.B[0] = s.B[0]; c.B[1] = s.B[1]; c.B[2] = s.B[2];
+  c.Bt[0] = s.Bt[0]; c.Bt[1] = s.Bt[1]; c.Bt[2] = s.Bt[2];
   for (int k = 0; k < 2; k++) {
     double mn = dunkey(s.jmin_key[k]), mx = dunkey(s.jmax_key[k]);
     c.jmin[k] = mn;
@@ -378,7 +382,7 @@ struct PolGF1a {
     double range = (double)sh->fc.range;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
       int c = i >> 8, k = i & 255;
-      double t = 1.0 - ((double)k / range) / sh->fc.B[c];     // transmission_map (BGDehaze.py:35-36)
+      double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
       sh->pT[c][k] = (t < g.tmin) ? g.tmin : t;              // np.maximum(t, tmin) (NaN stays NaN)
     }
     epsN_k = g.eps * range * range;
@@ -872,8 +876,14 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
       attr = smem;
     }
     UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, wmax, fs, d_m, d_part);
+    UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 1, wmax == WK_TWIN ? 1 : 0);
+    if (wmax != WK_TWIN) {
+      // refined_t() is always called without w (BGDehaze.py:52): the transmission uses the
+      // background light of a 15x15 window even when Background_light for J uses another w
+      UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, WK_TWIN, fs, d_m, d_part);
+      UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 0, 1);
+    }
   }
-  UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs);
   if (dbg && dbg->stop_after == 1) return UWIP_OK;
   if (dbg && dbg->t_raw) {
     dim3 g2(cdiv(W, 256), H);
