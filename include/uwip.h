@@ -192,6 +192,13 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
 int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n_frames, int width,
                     int height, const uwip_chain_params* p);
 
+/* per-frame status of the LAST uwip_chain_bgr8[_dev] / uwip_bgdehaze_bgr8_dev call on this context
+ * (synchronises the stream).  UWIP_FRAME_NAN: the reference's adaptiveExp_map is NaN for the whole
+ * frame (S = 0/0 where Yi = Yj = 0, BGDehaze.py:83, spreads through the box filters and the final
+ * min-max) - the 8-bit output is then all zeros, exactly what imwrite would store. */
+#define UWIP_FRAME_NAN 1
+int uwip_last_frame_flags(uwip_ctx* ctx, int n_frames, int32_t* flags_host);
+
 /* ---- synthetic input + checksums ------------------------------------------------- */
 /* frames first_frame .. first_frame+n_frames-1 of the integer-only generator (twin of
  * oracle/uwip_oracle.py:synth_frame) written to device memory. */

@@ -236,6 +236,22 @@ def test_chain_batch_matches_single_and_device_path(ctx):
     assert (staged == host).all()
     want = np.stack([O.chain_frame(f) for f in frames])
     assert np.abs(host.astype(int) - want.astype(int)).max() <= 1
+    assert (ctx.last_frame_flags(n) == 0).all()
+
+
+def test_chain_nan_frame_matches_reference(ctx):
+    """D9: where Yi = Yj = 0 the reference's S is 0/0 and the whole frame turns NaN (imwrite stores zeros).
+    The CUDA path must flag exactly the frames the oracle does."""
+    W, H = 320, 180
+    frames = np.stack([O.synth_frame(0x5EED0004, i, W, H) for i in range(3, 8)])  # frame 5 is a NaN frame
+    got = ctx.chain(frames)
+    flags = ctx.last_frame_flags(len(frames))
+    assert flags[2] == 1 and flags.sum() == 1
+    for i, fr in enumerate(frames):
+        b = O.aclahe_frame(O.histretch_frame(fr, "V", 1, 99), 2.0, 8, 8)
+        out, out8 = O.bgdehaze_frame(b, 15)
+        assert bool(flags[i] & 1) == bool(np.isnan(out).any()), i
+        assert np.abs(got[i].astype(int) - out8.astype(int)).max() <= 1
 
 
 def test_chain_full_size_properties(ctx):
@@ -251,9 +267,15 @@ def test_chain_full_size_properties(ctx):
     ctx.chain_dev(d_in, d_out, n, W, H)
     ctx.synchronize()
     out = d_out.cpu().numpy()
-    # the final min-max normalisation pins the extremes of every frame
+    flags = ctx.last_frame_flags(n)
+    # the final min-max normalisation pins the extremes of every frame; a frame on which the reference's
+    # exposure map is NaN (S = 0/0) comes out all zero, as imwrite would store it
     for i in range(n):
-        assert out[i].min() == 0 and out[i].max() == 255
+        if flags[i] & 1:
+            assert out[i].max() == 0
+        else:
+            assert out[i].min() == 0 and out[i].max() == 255
+    assert (flags & 1).sum() < n
     # determinism + batch independence: frame 1 alone gives the same bytes
     d_o1 = torch.empty_like(d_in[1:2])
     ctx.chain_dev(d_in[1:2].contiguous(), d_o1, 1, W, H)

@@ -218,6 +218,12 @@ class Context:
         p = params or self.chain_params()
         self._ck(self.lib.uwip_chain_bgr8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, C.byref(p)))
 
+    def last_frame_flags(self, n):
+        """Per-frame status of the last batched chain / bgdehaze call: 1 = the reference output is NaN (D9)."""
+        out = np.empty(n, np.int32)
+        self._ck(self.lib.uwip_last_frame_flags(self.h, int(n), _ptr(out)))
+        return out
+
     def histretch_dev(self, d_src, d_dst, n, width, height, channels="V", lo=2, hi=98, order="intended", hsv_round="cv2"):
         self._ck(self.lib.uwip_histretch_bgr8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, channels.encode(), lo, hi,
                                                   ORDER[order], HSV_ROUND[hsv_round]))

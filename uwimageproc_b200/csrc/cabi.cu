@@ -468,6 +468,12 @@ int uwip_bgdehaze_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t sp, uint8_t* ds
   return dehaze_host(ctx, src, sp, w, h, p, 0, dst8, dp, nullptr, nullptr, nullptr, nullptr, nullptr, out_f64);
 }
 
+static int32_t* flags_get(uwip_ctx* ctx, int n) {
+  int32_t* f = (int32_t*)uwip_slot(ctx, SLOT_FLAGS, sizeof(int32_t) * (size_t)n);
+  ctx->flags_n = f ? n : 0;
+  return f;
+}
+
 // sub-batch size so that the dehaze workspace (49 B/px/frame) stays below ~12 GB
 static int sub_batch(int n, int w, int h) {
   size_t per_frame = (size_t)w * h * 52;
@@ -483,18 +489,19 @@ int uwip_bgdehaze_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, 
   if (pp) p = *pp; else uwip_dehaze_defaults(&p);
   int nb = sub_batch(n, w, h);
   FrameState* fs = frame_state_get(ctx, nb);
-  if (!fs) return UWIP_ERR_NOMEM;
+  int32_t* flags = flags_get(ctx, n);
+  if (!fs || !flags) return UWIP_ERR_NOMEM;
   size_t fbytes = (size_t)w * h * 3;
   for (int i = 0; i < n; i += nb) {
     int m = std::min(nb, n - i);
     UWIP_CHECK(frame_state_reset(ctx, fs, m));
-    UWIP_CHECK(dehaze_frames_dev(ctx, d_src + (size_t)i * fbytes, d_dst + (size_t)i * fbytes, m, w, h, p, false, fs, nullptr));
+    UWIP_CHECK(dehaze_frames_dev(ctx, d_src + (size_t)i * fbytes, d_dst + (size_t)i * fbytes, m, w, h, p, false, fs, nullptr, flags + i));
   }
   return UWIP_OK;
 }
 
 // ---- the chain ------------------------------------------------------------------------------------------
-static int chain_sub(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int m, int w, int h, const uwip_chain_params& p, FrameState* fs) {
+static int chain_sub(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int m, int w, int h, const uwip_chain_params& p, FrameState* fs, int32_t* flags) {
   size_t fbytes = (size_t)w * h * 3;
   uint8_t* tmp = (uint8_t*)uwip_slot(ctx, SLOT_TMP_FRAME, fbytes * m);
   if (!tmp) return UWIP_ERR_NOMEM;
@@ -514,7 +521,7 @@ static int chain_sub(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int m,
     UWIP_CHECK(histretch_frames_dev(ctx, d_src, tmp, m, w, h, p.channels, p.lo, p.hi, p.order, p.hsv_round));
     UWIP_CHECK(aclahe_frames_dev(ctx, tmp, tmp, m, w, h, p.clip, p.tiles_x, p.tiles_y, p.hsv_round, nullptr, fs));
   }
-  return dehaze_frames_dev(ctx, tmp, d_dst, m, w, h, p.dehaze, true, fs, nullptr);
+  return dehaze_frames_dev(ctx, tmp, d_dst, m, w, h, p.dehaze, true, fs, nullptr, flags);
 }
 
 static int chain_check(uwip_ctx* ctx, const uwip_chain_params* p, int n, int w, int h) {
@@ -532,11 +539,12 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
   UWIP_CHECK(chain_check(ctx, p, n, w, h));
   int nb = sub_batch(n, w, h);
   FrameState* fs = frame_state_get(ctx, nb);
-  if (!fs) return UWIP_ERR_NOMEM;
+  int32_t* flags = flags_get(ctx, n);
+  if (!fs || !flags) return UWIP_ERR_NOMEM;
   size_t fbytes = (size_t)w * h * 3;
   for (int i = 0; i < n; i += nb) {
     int m = std::min(nb, n - i);
-    UWIP_CHECK(chain_sub(ctx, d_src + (size_t)i * fbytes, d_dst + (size_t)i * fbytes, m, w, h, *p, fs));
+    UWIP_CHECK(chain_sub(ctx, d_src + (size_t)i * fbytes, d_dst + (size_t)i * fbytes, m, w, h, *p, fs, flags + i));
   }
   return UWIP_OK;
 }
@@ -549,10 +557,11 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   int nb = sub_batch(n, w, h);
   nb = std::max(1, std::min(nb, (n + 1) / 2));  // at least two sub-batches so copies overlap compute
   FrameState* fs = frame_state_get(ctx, nb);
+  int32_t* flags = flags_get(ctx, n);
   size_t fbytes = (size_t)w * h * 3;
   uint8_t* din[2] = {(uint8_t*)uwip_slot(ctx, SLOT_CHAIN_IN0, fbytes * nb), (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_IN1, fbytes * nb)};
   uint8_t* dout[2] = {(uint8_t*)uwip_slot(ctx, SLOT_CHAIN_OUT0, fbytes * nb), (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_OUT1, fbytes * nb)};
-  if (!fs || !din[0] || !din[1] || !dout[0] || !dout[1]) return UWIP_ERR_NOMEM;
+  if (!fs || !flags || !din[0] || !din[1] || !dout[0] || !dout[1]) return UWIP_ERR_NOMEM;
   cudaStream_t s_in, s_out;
   UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
   UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
@@ -576,7 +585,7 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
     cudaEventRecord(ev_in[i], s_in);
     cudaStreamWaitEvent(ctx->stream, ev_in[i], 0);
     if (i >= 2) cudaStreamWaitEvent(ctx->stream, ev_out[i - 2], 0);  // out-buffer drained
-    rc = chain_sub(ctx, din[b], dout[b], m, w, h, *p, fs);
+    rc = chain_sub(ctx, din[b], dout[b], m, w, h, *p, fs, flags + (size_t)i * nb);
     cudaEventRecord(ev_comp[i], ctx->stream);
     cudaStreamWaitEvent(s_out, ev_comp[i], 0);
     cudaMemcpyAsync(dst + (size_t)i * nb * fbytes, dout[b], fbytes * m, cudaMemcpyDeviceToHost, s_out);
@@ -590,6 +599,15 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   if (rc != UWIP_OK) return rc;
   cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   if (e != cudaSuccess) { uwip_set_err(ctx, "chain pipeline: %s", cudaGetErrorString(e)); return UWIP_ERR_CUDA; }
+  return UWIP_OK;
+}
+
+int uwip_last_frame_flags(uwip_ctx* ctx, int n, int32_t* flags_host) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, flags_host && n > 0, "bad argument");
+  UWIP_REQUIRE(ctx, n <= ctx->flags_n, "more frames requested than the last batched call processed");
+  UWIP_CUDA(ctx, cudaMemcpyAsync(flags_host, ctx->slot_ptr[SLOT_FLAGS], sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return UWIP_OK;
 }
 

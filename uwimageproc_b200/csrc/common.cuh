@@ -35,6 +35,7 @@ struct uwip_ctx {
   size_t slot_bytes[kSlots] = {};
   void* pinned = nullptr;  // small pinned scratch for scalar results
   size_t pinned_bytes = 0;
+  int flags_n = 0;         // frames covered by SLOT_FLAGS (last batched chain / dehaze call)
 };
 
 enum Slot {
@@ -58,6 +59,7 @@ enum Slot {
   SLOT_CHAIN_OUT0,
   SLOT_CHAIN_OUT1,
   SLOT_SWEEP,
+  SLOT_FLAGS,         // per-frame status words of the last chain / dehaze call (int32)
 };
 
 const char* uwip_set_err(uwip_ctx* ctx, const char* fmt, ...);
@@ -279,7 +281,7 @@ struct DehazeDebug {  // optional float64 stage outputs for the stage-wise host 
   double* out = nullptr;      // [H*W*3]
   int stop_after = 0;         // 0 run all; 1 after background light; 2 after transmission; 3 after refined t; 4 after restored
 };
-int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, const uwip_dehaze_params& p, bool minmax_done, FrameState* fs, DehazeDebug* dbg);
+int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, const uwip_dehaze_params& p, bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags = nullptr);
 int frame_state_reset(uwip_ctx* ctx, FrameState* fs, int n);
 FrameState* frame_state_get(uwip_ctx* ctx, int n);
 

@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(256) exposure_minmax_kernel(GfCommon g, int W,
 }
 
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
-__global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, uint8_t* __restrict__ dst, double* dbg_out) {
+__global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
   size_t n_px = (size_t)W * H;
@@ -818,6 +818,7 @@ __global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, ui
   const FrameState& s = g.fs[f];
   double omn = dunkey(s.omin_key), den = dunkey(s.omax_key) - omn;
   bool nan_frame = s.nan_flag != 0;
+  if (flags && blockIdx.x == 0 && threadIdx.x == 0) flags[f] = nan_frame ? UWIP_FRAME_NAN : 0;
   const uint8_t* img = g.src + (size_t)f * n_px * 3;
   const float* J = g.J + (size_t)f * 2 * n_px;
   const float* refS = g.refS + (size_t)f * n_px;
@@ -844,7 +845,7 @@ __global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, ui
 // driver
 // -------------------------------------------------------------------------------------------------
 int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const uwip_dehaze_params& p,
-                      bool minmax_done, FrameState* fs, DehazeDebug* dbg) {
+                      bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags) {
   UWIP_REQUIRE(ctx, n >= 1 && W >= 1 && H >= 1, "bad size");
   UWIP_REQUIRE(ctx, p.window >= 1 && p.window <= WK_MAXWIN, "window must be 1..33");
   UWIP_REQUIRE(ctx, p.radius >= 1 && 2 * p.radius <= GF_NT - 64, "radius must be 1..160");
@@ -903,6 +904,6 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   if (dbg && dbg->stop_after == 4) return UWIP_OK;
   UWIP_CHECK(gf_launch<PolGF2a>(ctx, "dz_gf2a", gc, n, W, H, p.radius));
   UWIP_CHECK(gf_launch<PolGF2b>(ctx, "dz_gf2b", gc, n, W, H, p.radius));
-  UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, d_dst, dbg ? dbg->out : (double*)nullptr);
+  UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, d_dst, dbg ? dbg->out : (double*)nullptr, d_flags);
   return UWIP_OK;
 }
