@@ -30,7 +30,7 @@ struct uwip_ctx {
   std::vector<cudaEvent_t> ev_pool;
   std::string err;
   // named, grow-only device buffers
-  static const int kSlots = 24;
+  static const int kSlots = 32;
   void* slot_ptr[kSlots] = {};
   size_t slot_bytes[kSlots] = {};
   void* pinned = nullptr;  // small pinned scratch for scalar results
@@ -47,7 +47,7 @@ enum Slot {
   SLOT_TILELUT,       // per-frame per-tile CLAHE LUTs (u8)
   SLOT_FSTATE,        // FrameState[n]
   SLOT_TMP_FRAME,     // intermediate bgr8 frames
-  SLOT_MPLANES,       // dehaze: window-min planes (u8 x2)
+  SLOT_MPLANES,       // dehaze: window-min plane of green (u8)
   SLOT_PARTIALS,      // dehaze: per-block arg-min partials
   SLOT_AB,            // dehaze: guided-filter coefficient planes (f32 x8)
   SLOT_J,             // dehaze: J_blue, J_green (f32 x2)
@@ -60,6 +60,9 @@ enum Slot {
   SLOT_CHAIN_OUT1,
   SLOT_SWEEP,
   SLOT_FLAGS,         // per-frame status words of the last chain / dehaze call (int32)
+  SLOT_KQ,            // dehaze: packed k'_b k'_g k'_r m'_b (u32)
+  SLOT_YCC,           // dehaze: packed Yi Cri Cbi Yj (u32)
+  SLOT_STAB,          // dehaze: exposure-ratio table (f64 x 65536 per frame)
 };
 
 const char* uwip_set_err(uwip_ctx* ctx, const char* fmt, ...);

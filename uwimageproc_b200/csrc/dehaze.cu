@@ -4,20 +4,25 @@
 //              modules/bgdehaze/main.py:16-19.  Stage names D0..D10 follow SURVEY.md 8a.
 //
 // Data flow per frame (all frame-global reductions land in FrameState, no host round trips):
-//   minmax (D0)  ->  window max / arg-min partials / window-min planes (D1,D2)  ->  background light
-//   -> GF1a: strip-march box sums of 17 moments + per-pixel 3x3 solve -> a,b planes (f32 x8)
+//   minmax (D0)  ->  window: 15x15 window max / arg-min partials (D1), window min (D2), and the packed
+//                    plane kq = (k'_b, k'_g, k'_r, m'_b) + plane m'_g that every later pass reads
+//   -> GF1a: box sums of 17 moments + per-pixel 3x3 solve -> a,b planes (f32 x8)
 //   -> GF1b: box(a,b) -> refined t (D3,D5) -> J (D6) + min/max/sum reductions -> J planes (f32 x2)
-//   -> E: restored -> R8/I8 -> YCrCb joint min/max (D7,D8 first half)
-//   -> GF2a: S map + 13 moments + solve -> a,b (f32 x4)   -> GF2b: box(a,b) -> refined S, exposure min/max
+//   -> E: restored -> R8/I8 -> YCrCb joint min/max (D7,D8 first half); packed plane ycc = (Yi,Cri,Cbi,Yj)
+//   -> S table (256x256 f64 per frame: the exposure ratio is a function of two bytes)
+//   -> GF2a: S + 13 moments + solve -> a,b (f32 x4)   -> GF2b: box(a,b) -> refined S, exposure min/max
 //   -> final: normalise, x255, rint, saturate -> bgr8 (D8 second half, D10)
 //
-// The guided filter's (2r+1)^2 box sums are computed by a "strip march": a CTA owns a strip of image
-// columns (one thread per column, halo included), walks down the rows keeping the vertical running
-// sums in registers (add the entering row, subtract the leaving row), and for every output row turns
-// them into horizontal window sums through a two-level prefix scan in shared memory.  Guide moments
-// are exact 32-bit integers (the guide is k/range with k uint8); everything involving the filtered
-// signal accumulates in fp64.  The per-pixel solve works in "k units" (guide not divided by range)
-// with eps_k = eps*range^2, on the exact integer numerators N*S_ij - S_i*S_j.
+// Box sums ("quad march").  A CTA owns a strip of image columns (halo of r columns on both sides) and
+// walks down the rows.  Every thread owns FOUR adjacent columns: the vertical running sums of all
+// moments stay in registers (add the entering row, subtract the leaving row).  For every output row a
+// thread publishes the inclusive prefix over its own quad (one 16-byte shared store per moment) and
+// the quad total; a few threads turn the quad totals into a prefix over the strip; the window sum of
+// column 4t+c is then  G[t+r/4-1] - G[t-r/4-1] - quad[t-r/4][c-1] + quad[t+r/4][c]  (two 16-byte and
+// two 4-byte shared loads per moment for four pixels).  Guide moments are exact 32-bit integers (the
+// guide is k/range with k uint8); everything involving the filtered signal accumulates in fp64.  The
+// per-pixel solve works in "k units" (guide not divided by range) with eps_k = eps*range^2 on the
+// exact integer numerators N*S_ij - S_i*S_j.
 #include <algorithm>
 
 #include "common.cuh"
@@ -43,6 +48,23 @@ int frame_state_reset(uwip_ctx* ctx, FrameState* fs, int n) {
   return UWIP_OK;
 }
 FrameState* frame_state_get(uwip_ctx* ctx, int n) { return (FrameState*)uwip_slot(ctx, SLOT_FSTATE, sizeof(FrameState) * (size_t)n); }
+
+// ------------------------------------------------------------------------------------------------
+// small fp64 helpers
+// ------------------------------------------------------------------------------------------------
+// exact uint32 -> double without the conversion pipe (u < 2^32): 2^52 + u, minus 2^52
+__device__ __forceinline__ double u2d(uint32_t u) { return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0; }
+// 1/x to ~1 ulp (MUFU seed + two Newton steps).  Used where the result feeds continuous arithmetic
+// only; every place whose result is truncated to a byte uses the IEEE division.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // D0: joint min / max over all channels (bgdehaze/main.py:17)
@@ -76,7 +98,7 @@ __global__ void __launch_bounds__(256) minmax_kernel(const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// D1 / D2: 15x15 window max (3 channels) -> arg-min partials; window min (blue, green) -> m planes
+// D1 / D2: 15x15 window max (3 channels) -> arg-min partials; window min (blue, green); packed planes
 // ------------------------------------------------------------------------------------------------
 constexpr int WK_TX = 64, WK_TY = 32, WK_THREADS = 256;
 constexpr int WK_MAXWIN = 33;
@@ -89,9 +111,12 @@ struct ArgPartial {
 
 __device__ __forceinline__ bool lex_less(double a, unsigned ia, double b, unsigned ib) { return (a < b) || (a == b && ia < ib); }
 
-__global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __restrict__ src, int W, int H, int wmax,
-                                                            const FrameState* __restrict__ fs, uint8_t* __restrict__ mplanes,
-                                                            ArgPartial* __restrict__ partials) {
+// kq[y][x] = k'_b | k'_g<<8 | k'_r<<16 | m'_b<<24,  mg[y][x] = m'_g   (pitch Wp, pad columns zero)
+//   k' = k - kmin (bgdehaze/main.py:17 numerator), m' = window min - kmin, 0 where the zero padding of
+//   transmission_map (BGDehaze.py:32) reaches into the window.
+__global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __restrict__ src, int W, int H, int Wp, int wmax,
+                                                            const FrameState* __restrict__ fs, uint32_t* __restrict__ kq,
+                                                            uint8_t* __restrict__ mgp, ArgPartial* __restrict__ partials) {
   extern __shared__ uint32_t s_w[];
   __shared__ double s_nrm[256];
   __shared__ ArgPartial s_part[WK_THREADS / 32];
@@ -135,25 +160,32 @@ __global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __res
   unsigned bi0 = 0xffffffffu, bi1 = 0xffffffffu;
   bool have = false;
   int gx = x0 + x;
+  uint32_t* kqf = kq + (size_t)f * Wp * H;
+  uint8_t* mgf = mgp + (size_t)f * Wp * H;
   for (int j = 0; j < WK_TY / (WK_THREADS / WK_TX); j++) {
     int yy = rg * (WK_TY / (WK_THREADS / WK_TX)) + j;
     int gy = y0 + yy;
-    if (gx >= W || gy >= H) continue;
+    if (gx >= Wp || gy >= H) continue;
+    size_t ppix = (size_t)gy * Wp + gx;
+    if (gx >= W) { kqf[ppix] = 0u; mgf[ppix] = 0; continue; }
     uint32_t m0 = 0, m1 = 0, n0 = 0xffffffffu;
     for (int k = -pmax; k < wmax - pmax; k++) {
       m0 = __vmaxu2(m0, HX0[(yy + PL + k) * WK_TX + x]);
       m1 = max(m1, HX1[(yy + PL + k) * WK_TX + x]);
     }
     for (int k = -pmin; k < wmin - pmin; k++) n0 = __vminu2(n0, HN0[(yy + PL + k) * WK_TX + x]);
-    size_t pix = (size_t)gy * W + gx;
-    uint8_t* mp = mplanes + (size_t)f * 2 * W * H;
-    mp[pix] = (uint8_t)(n0 & 0xffffu);
-    mp[(size_t)W * H + pix] = (uint8_t)(n0 >> 16);
+    const int pw = WK_TWIN / 2;
+    bool touches = (gx < pw) || (gy < pw) || (gx - pw + WK_TWIN - 1 >= W) || (gy - pw + WK_TWIN - 1 >= H);
+    uint32_t c0 = P0[(yy + PL) * RW + x + PL], c1 = P1[(yy + PL) * RW + x + PL];
+    uint32_t mb = touches ? 0u : (n0 & 0xffffu) - (uint32_t)kmin;
+    uint32_t mg = touches ? 0u : (n0 >> 16) - (uint32_t)kmin;
+    kqf[ppix] = ((c0 & 0xffffu) - kmin) | (((c0 >> 16) - kmin) << 8) | ((c1 - kmin) << 16) | (mb << 24);
+    mgf[ppix] = (uint8_t)mg;
     // D (BGDehaze.py:20-21): max_R - max_B, max_R - max_G on the normalised image, in fp64
     double nr = s_nrm[(int)m1 - kmin];
     double d0 = nr - s_nrm[(int)(m0 & 0xffffu) - kmin];
     double d1 = nr - s_nrm[(int)(m0 >> 16) - kmin];
-    unsigned idx = (unsigned)pix;
+    unsigned idx = (unsigned)((size_t)gy * W + gx);
     if (!have) { bd0 = d0; bd1 = d1; bi0 = bi1 = idx; have = true; }
     else {
       if (d0 < bd0) { bd0 = d0; bi0 = idx; }
@@ -232,43 +264,33 @@ __global__ void __launch_bounds__(256) bglight_finish_kernel(const uint8_t* __re
 }
 
 // transmission_map output for the stage-wise API: t = 1 - min_window(I_c / B_c), zero padded
-__global__ void traw_kernel(const uint8_t* __restrict__ mplanes, int W, int H, const FrameState* __restrict__ fs,
-                            double* __restrict__ t_raw) {
+__global__ void traw_kernel(const uint32_t* __restrict__ kq, const uint8_t* __restrict__ mgp, int W, int H, int Wp,
+                            const FrameState* __restrict__ fs, double* __restrict__ t_raw) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W) return;
   const FrameState& s = fs[0];
-  int kmin = s.kmin;
-  double range = (double)((int)s.kmax - kmin);
-  const int pw = WK_TWIN / 2;
-  bool touches = (x < pw) || (y < pw) || (x - pw + WK_TWIN - 1 >= W) || (y - pw + WK_TWIN - 1 >= H);
-  size_t pix = (size_t)y * W + x;
-  for (int c = 0; c < 2; c++) {
-    int m = touches ? 0 : (int)mplanes[(size_t)c * W * H + pix] - kmin;
-    t_raw[(size_t)c * W * H + pix] = 1.0 - ((double)m / range) / s.Bt[c];
-  }
+  double range = (double)((int)s.kmax - (int)s.kmin);
+  size_t pp = (size_t)y * Wp + x, pix = (size_t)y * W + x;
+  int mb = (int)(kq[pp] >> 24), mg = (int)mgp[pp];
+  t_raw[pix] = 1.0 - ((double)mb / range) / s.Bt[0];
+  t_raw[(size_t)W * H + pix] = 1.0 - ((double)mg / range) / s.Bt[1];
 }
 
 // ------------------------------------------------------------------------------------------------
-// strip-march box-sum engine
+// guided-filter helpers
 // ------------------------------------------------------------------------------------------------
-constexpr int GF_NT = 384;                              // threads = strip columns incl. 2r halo
-constexpr int GF_SEG = 24;                              // columns per scan segment
-constexpr int GF_NSEG = GF_NT / GF_SEG;                 // 16 segments
-constexpr int GF_PITCH = GF_SEG * (GF_NSEG + 1);        // column c lives at (c % SEG) * 17 + c / SEG
-static_assert(GF_NSEG == 16, "phase-1 warp layout assumes 16 segments");
-
 // 3x3 symmetric solve shared by GF1a / GF2a.  Inputs are window sums in k units:
 //   S[3] (sum k_i), SS[6] (sum k_i k_j: 00 01 02 11 12 22), N (window pixel count),
 //   Sp (sum p), Sip[3] (sum k_i p).  Output a[3] (k units) and b.
 __device__ __forceinline__ void gf_build_M(const uint32_t* si, double N, double epsN2, double* M, double* Sd) {
-  Sd[0] = (double)si[0]; Sd[1] = (double)si[1]; Sd[2] = (double)si[2];
+  Sd[0] = u2d(si[0]); Sd[1] = u2d(si[1]); Sd[2] = u2d(si[2]);
   // exact: N*S_ij and S_i*S_j are integers < 2^53
-  M[0] = fma(N, (double)si[3], -Sd[0] * Sd[0]) + epsN2;
-  M[1] = fma(N, (double)si[4], -Sd[0] * Sd[1]);
-  M[2] = fma(N, (double)si[5], -Sd[0] * Sd[2]);
-  M[3] = fma(N, (double)si[6], -Sd[1] * Sd[1]) + epsN2;
-  M[4] = fma(N, (double)si[7], -Sd[1] * Sd[2]);
-  M[5] = fma(N, (double)si[8], -Sd[2] * Sd[2]) + epsN2;
+  M[0] = fma(N, u2d(si[3]), -Sd[0] * Sd[0]) + epsN2;
+  M[1] = fma(N, u2d(si[4]), -Sd[0] * Sd[1]);
+  M[2] = fma(N, u2d(si[5]), -Sd[0] * Sd[2]);
+  M[3] = fma(N, u2d(si[6]), -Sd[1] * Sd[1]) + epsN2;
+  M[4] = fma(N, u2d(si[7]), -Sd[1] * Sd[2]);
+  M[5] = fma(N, u2d(si[8]), -Sd[2] * Sd[2]) + epsN2;
 }
 // adjugate of the symmetric matrix [[m0 m1 m2],[m1 m3 m4],[m2 m4 m5]] and 1/det
 __device__ __forceinline__ void gf_adjugate(const double* M, double* A, double& rdet) {
@@ -279,7 +301,7 @@ __device__ __forceinline__ void gf_adjugate(const double* M, double* A, double& 
   A[4] = M[1] * M[2] - M[0] * M[4];
   A[5] = M[0] * M[3] - M[1] * M[1];
   double det = M[0] * A[0] + M[1] * A[1] + M[2] * A[2];
-  rdet = 1.0 / det;
+  rdet = rcp_fast(det);
 }
 __device__ __forceinline__ void gf_solve(const double* A, double rdet, const double* Sd, double N, double invN, double Sp,
                                          const double* Sip, double* a, double& b) {
@@ -292,22 +314,36 @@ __device__ __forceinline__ void gf_solve(const double* A, double rdet, const dou
 }
 
 struct GfCommon {
-  const uint8_t* src;     // bgr8 frames
-  const uint8_t* mplanes; // [n][2][H*W]
-  float* ab;              // [n][8][H*W]
-  float* J;               // [n][2][H*W]
-  float* refS;            // [n][H*W]
+  const uint32_t* kq;     // [n][H][Wp] packed k'_b k'_g k'_r m'_b
+  const uint8_t* mg;      // [n][H][Wp] m'_g
+  uint32_t* ycc;          // [n][H][Wp] packed Yi Cri Cbi Yj
+  const double* stab;     // [n][256][256] exposure ratio S(yi', yj')
+  float* ab;              // [n][8][H][Wp]
+  float* J;               // [n][2][H][Wp]
+  float* refS;            // [n][H][Wp]
   FrameState* fs;
   double eps, tmin;
   double* dbg_tref;       // optional [2][H*W] (frame 0 only)
+};
+
+// strip geometry of one launch (see the file header)
+struct GfGeom {
+  int W, H, Wp;   // image size; pitch of the internal planes (multiple of 4)
+  int r;          // box radius
+  int HL;         // halo rounded up to a multiple of 4
+  int SW;         // output columns per strip (multiple of 4)
+  int NQ;         // quads per strip: one zero guard quad + (2*HL + SW)/4
+  int SEGQ, GP;   // quads per scan segment; pitch of the quad-total rows (8*SEGQ >= NQ)
+  int seg_h;      // output rows per vertical segment
+  int fast;       // r % 4 == 0: window edges fall on quad boundaries
 };
 
 // ---- shared per-CTA frame constants --------------------------------------------------------------
 struct FrameConst {
   int kmin, range;
   double B[3], Bt[3];
-  // restored-image parameters (valid after GF1b): J min / 1/(max-min), red LUT scalars
-  double jmin[2], jinv[2];
+  // restored-image parameters (valid after GF1b): J min / (max-min)
+  double jmin[2], jinv[2], jrcp[2];
   int yi_min, yi_rng, yj_min, yj_rng;
 };
 
@@ -320,6 +356,7 @@ __device__ __forceinline__ void load_frame_const(const FrameState& s, FrameConst
     double mn = dunkey(s.jmin_key[k]), mx = dunkey(s.jmax_key[k]);
     c.jmin[k] = mn;
     c.jinv[k] = mx - mn;  // denominator; divisions are done where used
+    c.jrcp[k] = 1.0 / (mx - mn);
   }
   c.yi_min = s.yi_min; c.yi_rng = (int)s.yi_max - (int)s.yi_min;
   c.yj_min = s.yj_min; c.yj_rng = (int)s.yj_max - (int)s.yj_min;
@@ -355,76 +392,21 @@ __device__ void build_red_tables(const FrameState& s, const FrameConst& fc, doub
   }
 }
 
-// restored blue / green from the stored J value (dehazed_BG, BGDehaze.py:53-56)
-__device__ __forceinline__ double norm_j(float j, const FrameConst& fc, int c) { return ((double)j - fc.jmin[c]) / fc.jinv[c]; }
-
-// -------------------------------------------------------------------------------------------------
-// policies
-// -------------------------------------------------------------------------------------------------
-// GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
-struct PolGF1a {
-  static constexpr int NI = 9, ND = 8;
-  struct Shared {
-    double pT[2][256];  // p_c as a function of the window-min k'
-    FrameConst fc;
-  };
-  GfCommon g; Shared* sh; int W, H, f;
-  const uint8_t* img; const uint8_t* mp; float* ab;
-  double epsN_k;  // eps * range^2
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, int W_, int H_) {
-    g = gc; sh = s; W = W_; H = H_; f = frame;
-    size_t n_px = (size_t)W * H;
-    img = g.src + (size_t)f * n_px * 3;
-    mp = g.mplanes + (size_t)f * 2 * n_px;
-    ab = g.ab + (size_t)f * 8 * n_px;
-    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
-    __syncthreads();
-    double range = (double)sh->fc.range;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-      int c = i >> 8, k = i & 255;
-      double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
-      sh->pT[c][k] = (t < g.tmin) ? g.tmin : t;              // np.maximum(t, tmin) (NaN stays NaN)
-    }
-    epsN_k = g.eps * range * range;
-    __syncthreads();
-  }
-  template <int SIGN>
-  __device__ __forceinline__ void accum(int y, int x, uint32_t* Vi, double* Vd) const {
-    size_t pix = (size_t)y * W + x;
-    const uint8_t* p = img + pix * 3;
-    int kmin = sh->fc.kmin;
-    int kb = (int)p[0] - kmin, kg = (int)p[1] - kmin, kr = (int)p[2] - kmin;
-    const int pw = WK_TWIN / 2;
-    bool touches = (x < pw) || (y < pw) || (x - pw + WK_TWIN - 1 >= W) || (y - pw + WK_TWIN - 1 >= H);
-    int mb = touches ? 0 : (int)mp[pix] - kmin;
-    int mg = touches ? 0 : (int)mp[(size_t)W * H + pix] - kmin;
-    double pb = sh->pT[0][mb], pg = sh->pT[1][mg];
-    int sb = SIGN * kb, sg = SIGN * kg, sr = SIGN * kr;
-    Vi[0] += sb; Vi[1] += sg; Vi[2] += sr;
-    Vi[3] += sb * kb; Vi[4] += sb * kg; Vi[5] += sb * kr;
-    Vi[6] += sg * kg; Vi[7] += sg * kr; Vi[8] += sr * kr;
-    double db = (double)sb, dg = (double)sg, dr = (double)sr;
-    Vd[0] += (SIGN > 0 ? pb : -pb);
-    Vd[1] += (SIGN > 0 ? pg : -pg);
-    Vd[2] = fma(db, pb, Vd[2]); Vd[3] = fma(dg, pb, Vd[3]); Vd[4] = fma(dr, pb, Vd[4]);
-    Vd[5] = fma(db, pg, Vd[5]); Vd[6] = fma(dg, pg, Vd[6]); Vd[7] = fma(dr, pg, Vd[7]);
-  }
-  __device__ __forceinline__ void epilogue(int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
-    double N = (double)Ncnt, invN = 1.0 / N;
-    double M[6], Sd[3], A[6], rdet;
-    gf_build_M(si, N, epsN_k * N * N, M, Sd);
-    gf_adjugate(M, A, rdet);
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-    double a[3], b;
-    gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
-    ab[0 * n_px + pix] = (float)a[0]; ab[1 * n_px + pix] = (float)a[1]; ab[2 * n_px + pix] = (float)a[2]; ab[3 * n_px + pix] = (float)b;
-    gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
-    ab[4 * n_px + pix] = (float)a[0]; ab[5 * n_px + pix] = (float)a[1]; ab[6 * n_px + pix] = (float)a[2]; ab[7 * n_px + pix] = (float)b;
-  }
-  __device__ void finish() {}
+struct ExpShared {
+  RedTables rt;
+  FrameConst fc;
 };
+__device__ void exp_shared_init(ExpShared* sh, const FrameState& s, double n_px) {
+  if (threadIdx.x == 0) load_frame_const(s, sh->fc);
+  __syncthreads();
+  build_red_tables(s, sh->fc, n_px, &sh->rt, threadIdx.x, blockDim.x);
+  __syncthreads();
+}
+// restored blue / green from the stored J value (dehazed_BG, BGDehaze.py:53-56).  The IEEE division is
+// what the bytes R8 are truncated from; the reciprocal flavour feeds products only.
+__device__ __forceinline__ double norm_j(float j, const FrameConst& fc, int c) { return ((double)j - fc.jmin[c]) / fc.jinv[c]; }
+__device__ __forceinline__ double norm_j_fast(float j, const FrameConst& fc, int c) { return ((double)j - fc.jmin[c]) * fc.jrcp[c]; }
 
-// block-wide reductions used by the epilogue policies
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d); v = o < v ? o : v; }
@@ -440,78 +422,216 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
 }
+__device__ __forceinline__ float warp_min_f32(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_min_f64(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t quad_get(const uint4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float quad_get(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+
+
+// V-phase of the plane-reading policies (GF1b, GF2b): one plane at a time so that only two quads are
+// in flight per plane; every value goes through fp64 (the a,b planes are f32).
+template <int NP>
+__device__ __forceinline__ void gf_accum_planes(const float* __restrict__ base, size_t n_pp, size_t oE, size_t oL, bool enter, bool leave,
+                                                unsigned cmask, double (&Vd)[4][NP]) {
+#pragma unroll
+  for (int k = 0; k < NP; k++) {
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f), l = e;
+    if (enter) e = __ldg(reinterpret_cast<const float4*>(base + k * n_pp + oE));
+    if (leave) l = __ldg(reinterpret_cast<const float4*>(base + k * n_pp + oL));
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (cmask & (1u << c)) Vd[c][k] += (double)quad_get(e, c) - (double)quad_get(l, c);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// policies: what is accumulated per pixel (accum), and what is made of the window sums (column)
+// -------------------------------------------------------------------------------------------------
+constexpr int GF_NSEG = 8;    // scan segments per quad-total row
+
+// GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
+struct PolGF1a {
+  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224;
+  static constexpr bool PREFETCH = true;
+  struct Shared {
+    double pT[2][256];  // p_c as a function of the window-min k'
+    FrameConst fc;
+  };
+  struct Raw { uint4 k; uint32_t m; };
+  GfCommon g; Shared* sh; int Wp, H, f;
+  const uint32_t* kq; const uint8_t* mg; float* ab;
+  double epsN_k;  // eps * range^2
+  float o[2][8];
+  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
+    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
+    size_t n_pp = (size_t)Wp * H;
+    kq = g.kq + (size_t)f * n_pp;
+    mg = g.mg + (size_t)f * n_pp;
+    ab = g.ab + (size_t)f * 8 * n_pp;
+    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
+    __syncthreads();
+    double range = (double)sh->fc.range;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      int c = i >> 8, k = i & 255;
+      double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
+      sh->pT[c][k] = (t < g.tmin) ? g.tmin : t;              // np.maximum(t, tmin) (NaN stays NaN)
+    }
+    epsN_k = g.eps * range * range;
+    __syncthreads();
+  }
+  __device__ __forceinline__ void zero(Raw& r) const { r.k = make_uint4(0, 0, 0, 0); r.m = 0; }
+  __device__ __forceinline__ void load(int y, int gx, Raw& r) const {
+    size_t o = (size_t)y * Wp + gx;
+    r.k = __ldg(reinterpret_cast<const uint4*>(kq + o));
+    r.m = __ldg(reinterpret_cast<const uint32_t*>(mg + o));
+  }
+  template <int SIGN>
+  __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI > 0 ? NI : 1], double (&Vd)[4][ND]) const {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t w = quad_get(r.k, c);
+      uint32_t kb = w & 255u, kg = (w >> 8) & 255u, kr = (w >> 16) & 255u, mb = w >> 24, mgv = (r.m >> (8 * c)) & 255u;
+      if (SIGN > 0) {
+        Vi[c][0] += kb; Vi[c][1] += kg; Vi[c][2] += kr;
+        Vi[c][3] += kb * kb; Vi[c][4] += kb * kg; Vi[c][5] += kb * kr;
+        Vi[c][6] += kg * kg; Vi[c][7] += kg * kr; Vi[c][8] += kr * kr;
+      } else {
+        Vi[c][0] -= kb; Vi[c][1] -= kg; Vi[c][2] -= kr;
+        Vi[c][3] -= kb * kb; Vi[c][4] -= kb * kg; Vi[c][5] -= kb * kr;
+        Vi[c][6] -= kg * kg; Vi[c][7] -= kg * kr; Vi[c][8] -= kr * kr;
+      }
+      if (cmask & (1u << c)) {
+        double pb = sh->pT[0][mb], pg = sh->pT[1][mgv];
+        if (SIGN < 0) { pb = -pb; pg = -pg; }
+        double db = u2d(kb), dg = u2d(kg), dr = u2d(kr);
+        Vd[c][0] += pb;
+        Vd[c][1] += pg;
+        Vd[c][2] = fma(db, pb, Vd[c][2]); Vd[c][3] = fma(dg, pb, Vd[c][3]); Vd[c][4] = fma(dr, pb, Vd[c][4]);
+        Vd[c][5] = fma(db, pg, Vd[c][5]); Vd[c][6] = fma(dg, pg, Vd[c][6]); Vd[c][7] = fma(dr, pg, Vd[c][7]);
+      }
+    }
+  }
+  __device__ __forceinline__ void row_begin(int, int) {}
+  __device__ __forceinline__ void column(int cc, int, int, int Ncnt, const uint32_t* si, const double* sd) {
+    double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
+    double M[6], Sd[3], A[6], rdet;
+    gf_build_M(si, N, epsN_k * N * N, M, Sd);
+    gf_adjugate(M, A, rdet);
+    double a[3], b;
+    gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
+    o[cc][0] = (float)a[0]; o[cc][1] = (float)a[1]; o[cc][2] = (float)a[2]; o[cc][3] = (float)b;
+    gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
+    o[cc][4] = (float)a[0]; o[cc][5] = (float)a[1]; o[cc][6] = (float)a[2]; o[cc][7] = (float)b;
+  }
+  // both columns of the pair lie inside the padded pitch (Wp is a multiple of 4)
+  __device__ __forceinline__ void store_pair(int y, int x) {
+    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) *reinterpret_cast<float2*>(ab + k * n_pp + pp) = make_float2(o[0][k], o[1][k]);
+  }
+  __device__ void finish() {}
+};
 
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
-  static constexpr int NI = 0, ND = 8;
+  static constexpr int NI = 0, ND = 8, MINB = 2, MAXREG = 168, NT = 192;
+  static constexpr bool PREFETCH = false;
   struct Shared {
     double nrm[256];
     FrameConst fc;
   };
-  GfCommon g; Shared* sh; int W, H, f;
-  const uint8_t* img; const float* ab; float* J;
-  unsigned long long jmn[2], jmx[2]; long long jsum[2];
-  unsigned rmn, rmx; unsigned long long rsum; unsigned nanf;
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, int W_, int H_) {
-    g = gc; sh = s; W = W_; H = H_; f = frame;
-    size_t n_px = (size_t)W * H;
-    img = g.src + (size_t)f * n_px * 3;
-    ab = g.ab + (size_t)f * 8 * n_px;
-    J = g.J + (size_t)f * 2 * n_px;
+  struct Raw {};
+  GfCommon g; Shared* sh; int W, Wp, H, f;
+  const uint32_t* kq; const float* ab; float* J;
+  float jmn[2], jmx[2];
+  long long jsum[2];   // sum of bits(J*2^32 + 1.5*2^52): exact 2^-32 fixed point, independent of the partition
+  unsigned cnt, rmn, rmx, rsum, nanf;
+  uint4 krow;
+  float o[2][2];
+  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
+    g = gc; sh = s; W = gg.W; Wp = gg.Wp; H = gg.H; f = frame;
+    size_t n_pp = (size_t)Wp * H;
+    kq = g.kq + (size_t)f * n_pp;
+    ab = g.ab + (size_t)f * 8 * n_pp;
+    J = g.J + (size_t)f * 2 * n_pp;
     if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->nrm[i] = (double)i / (double)sh->fc.range;
-    jmn[0] = jmn[1] = ~0ull; jmx[0] = jmx[1] = 0; jsum[0] = jsum[1] = 0;
-    rmn = 255; rmx = 0; rsum = 0; nanf = 0;
+    jmn[0] = jmn[1] = __int_as_float(0x7f800000); jmx[0] = jmx[1] = -__int_as_float(0x7f800000);
+    jsum[0] = jsum[1] = 0;
+    cnt = 0; rmn = 255; rmx = 0; rsum = 0; nanf = 0;
     __syncthreads();
   }
-  template <int SIGN>
-  __device__ __forceinline__ void accum(int y, int x, uint32_t*, double* Vd) const {
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      double v = (double)__ldg(ab + k * n_px + pix);
-      Vd[k] += (SIGN > 0 ? v : -v);
-    }
+  __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
+    gf_accum_planes<8>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
   }
-  __device__ __forceinline__ void epilogue(int y, int x, int Ncnt, const uint32_t*, const double* sd) {
-    double invN = 1.0 / (double)Ncnt;
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-    const uint8_t* p = img + pix * 3;
-    int kmin = sh->fc.kmin;
-    int k[3] = {(int)p[0] - kmin, (int)p[1] - kmin, (int)p[2] - kmin};
-    double kd[3] = {(double)k[0], (double)k[1], (double)k[2]};
+  __device__ __forceinline__ void row_begin(int y, int gx) { krow = __ldg(reinterpret_cast<const uint4*>(kq + (size_t)y * Wp + gx)); }
+  __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd) {
+    double invN = rcp_fast(u2d((uint32_t)Ncnt));
+    uint32_t w = quad_get(krow, x & 3);
+    uint32_t k[3] = {w & 255u, (w >> 8) & 255u, (w >> 16) & 255u};
+    double kd[3] = {u2d(k[0]), u2d(k[1]), u2d(k[2])};
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       const double* s = sd + 4 * c;
       double q = (s[0] * kd[0] + s[1] * kd[1] + s[2] * kd[2] + s[3]) * invN;   // guidedfilter.py:100-101
-      if (g.dbg_tref && f == 0) g.dbg_tref[(size_t)c * n_px + pix] = q;
+      if (g.dbg_tref && f == 0) g.dbg_tref[(size_t)c * W * H + (size_t)y * W + x] = q;
       double Bc = sh->fc.B[c];
-      double Jv = (sh->nrm[k[c]] - Bc) / q + Bc;                              // BGDehaze.py:53,55
+      double Jv = (sh->nrm[k[c]] - Bc) * rcp_fast(q) + Bc;                    // BGDehaze.py:53,55
       float Jf = (float)Jv;
-      J[(size_t)c * n_px + pix] = Jf;
-      double Jr = (double)Jf;
-      if (!(fabs(Jr) < 1.0e6)) { nanf |= 1u; Jr = 0.0; }
-      unsigned long long key = dkey(Jr);
-      jmn[c] = key < jmn[c] ? key : jmn[c];
-      jmx[c] = key > jmx[c] ? key : jmx[c];
-      jsum[c] += __double2ll_rn(Jr * 4294967296.0);
+      o[cc][c] = Jf;
+      if (!(fabsf(Jf) < 262144.0f)) { nanf |= 1u; Jf = 0.f; }
+      jmn[c] = fminf(jmn[c], Jf);
+      jmx[c] = fmaxf(jmx[c], Jf);
+      jsum[c] += __double_as_longlong(fma((double)Jf, 4294967296.0, 6755399441055744.0));
     }
-    rmn = min(rmn, (unsigned)k[2]); rmx = max(rmx, (unsigned)k[2]); rsum += (unsigned)k[2];
+    cnt++;
+    rmn = min(rmn, k[2]); rmx = max(rmx, k[2]); rsum += k[2];
+  }
+  __device__ __forceinline__ void store_pair(int y, int x) {
+    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
+    *reinterpret_cast<float2*>(J + pp) = make_float2(o[0][0], o[1][0]);
+    *reinterpret_cast<float2*>(J + n_pp + pp) = make_float2(o[0][1], o[1][1]);
   }
   __device__ void finish() {
     FrameState& s = g.fs[f];
     for (int c = 0; c < 2; c++) {
-      unsigned long long a = warp_min_u64(jmn[c]), b = warp_max_u64(jmx[c]);
-      long long sm = warp_sum_i64(jsum[c]);
+      float a = warp_min_f32(jmn[c]), b = warp_max_f32(jmx[c]);
+      long long sm = warp_sum_i64(jsum[c] - (long long)cnt * __double_as_longlong(6755399441055744.0));
       if ((threadIdx.x & 31) == 0) {
-        atomicMin(&s.jmin_key[c], a);
-        atomicMax(&s.jmax_key[c], b);
+        if (a <= b) {
+          atomicMin(&s.jmin_key[c], dkey((double)a));
+          atomicMax(&s.jmax_key[c], dkey((double)b));
+        }
         atomicAdd((unsigned long long*)&s.jsum_fix[c], (unsigned long long)sm);
       }
     }
     unsigned a = warp_reduce_min_u32(rmn), b = warp_reduce_max_u32(rmx);
-    long long rs = warp_sum_i64((long long)rsum);
+    unsigned rs = __reduce_add_sync(0xffffffffu, rsum);
     unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
     if ((threadIdx.x & 31) == 0) {
       atomicMin(&s.rmin, a);
@@ -522,83 +642,70 @@ struct PolGF1b {
   }
 };
 
-// per-pixel guide / S evaluation shared by GF2a, GF2b, E and final
-struct ExpShared {
-  RedTables rt;
-  FrameConst fc;
-};
-struct PixelExp {
-  int gy, gcr, gcb;     // guide = YiCrCb - joint min (k units of normYiCrCb)
-  double rest[3];       // restored b, g, r
-  int yj;               // Yj - joint min of YjCrCb
-};
-__device__ __forceinline__ void restored_pixel(const ExpShared* sh, const uint8_t* p, float jb, float jg, double* rest, int* r8, int* i8) {
-  int kmin = sh->fc.kmin;
-  int kb = (int)p[0] - kmin, kg = (int)p[1] - kmin, kr = (int)p[2] - kmin;
-  rest[0] = norm_j(jb, sh->fc, 0);
-  rest[1] = norm_j(jg, sh->fc, 1);
-  rest[2] = sh->rt.redN[kr];
-  r8[0] = trunc_u8(rest[0] * 255.0); r8[1] = trunc_u8(rest[1] * 255.0); r8[2] = sh->rt.red8[kr];
-  i8[0] = sh->rt.i8[kb]; i8[1] = sh->rt.i8[kg]; i8[2] = sh->rt.i8[kr];
-}
-__device__ __forceinline__ void eval_pixel(const ExpShared* sh, const uint8_t* p, float jb, float jg, PixelExp& e) {
-  int r8[3], i8[3];
-  restored_pixel(sh, p, jb, jg, e.rest, r8, i8);
-  int Y, Cr, Cb;
-  bgr2ycrcb_u8(i8[0], i8[1], i8[2], Y, Cr, Cb);
-  e.gy = Y - sh->fc.yi_min; e.gcr = Cr - sh->fc.yi_min; e.gcb = Cb - sh->fc.yi_min;
-  bgr2ycrcb_u8(r8[0], r8[1], r8[2], Y, Cr, Cb);
-  e.yj = Y - sh->fc.yj_min;
-}
-__device__ void exp_shared_init(ExpShared* sh, const FrameState& s, double n_px) {
-  if (threadIdx.x == 0) load_frame_const(s, sh->fc);
-  __syncthreads();
-  build_red_tables(s, sh->fc, n_px, &sh->rt, threadIdx.x, blockDim.x);
-  __syncthreads();
-}
-
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
-  static constexpr int NI = 9, ND = 4;
-  typedef ExpShared Shared;
-  GfCommon g; Shared* sh; int W, H, f;
-  const uint8_t* img; const float* J; float* ab;
+  static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224;
+  static constexpr bool PREFETCH = true;
+  struct Shared { FrameConst fc; };
+  struct Raw { uint4 y; };
+  GfCommon g; Shared* sh; int Wp, H, f;
+  const uint32_t* ycc; const double* stab; float* ab;
+  uint32_t ysub;   // (yi_min, yi_min, yi_min, yj_min): no byte can borrow
   double epsN_k; unsigned nanf;
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, int W_, int H_) {
-    g = gc; sh = s; W = W_; H = H_; f = frame;
-    size_t n_px = (size_t)W * H;
-    img = g.src + (size_t)f * n_px * 3;
-    J = g.J + (size_t)f * 2 * n_px;
-    ab = g.ab + (size_t)f * 8 * n_px;
-    exp_shared_init(sh, g.fs[f], (double)n_px);
+  float o[2][4];
+  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
+    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
+    size_t n_pp = (size_t)Wp * H;
+    ycc = g.ycc + (size_t)f * n_pp;
+    stab = g.stab + (size_t)f * 65536;
+    ab = g.ab + (size_t)f * 8 * n_pp;
+    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
+    __syncthreads();
     double rng = (double)sh->fc.yi_rng;
     epsN_k = g.eps * rng * rng;
+    uint32_t a = (uint32_t)sh->fc.yi_min, b = (uint32_t)sh->fc.yj_min;
+    ysub = a | (a << 8) | (a << 16) | (b << 24);
     nanf = 0;
   }
+  __device__ __forceinline__ void zero(Raw& r) const { r.y = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void load(int y, int gx, Raw& r) const { r.y = __ldg(reinterpret_cast<const uint4*>(ycc + (size_t)y * Wp + gx)); }
   template <int SIGN>
-  __device__ __forceinline__ void accum(int y, int x, uint32_t* Vi, double* Vd) {
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-    PixelExp e;
-    eval_pixel(sh, img + pix * 3, __ldg(J + pix), __ldg(J + n_px + pix), e);
-    double yi = (double)e.gy / (double)sh->fc.yi_rng, yj = (double)e.yj / (double)sh->fc.yj_rng;
-    double yi2 = 0.3 * (yi * yi);
-    double S = (yj * yi + yi2) / (yj * yj + yi2);
-    if (SIGN > 0 && !(S == S)) nanf = 1u;
-    int s0 = SIGN * e.gy, s1 = SIGN * e.gcr, s2 = SIGN * e.gcb;
-    Vi[0] += s0; Vi[1] += s1; Vi[2] += s2;
-    Vi[3] += s0 * e.gy; Vi[4] += s0 * e.gcr; Vi[5] += s0 * e.gcb;
-    Vi[6] += s1 * e.gcr; Vi[7] += s1 * e.gcb; Vi[8] += s2 * e.gcb;
-    Vd[0] += (SIGN > 0 ? S : -S);
-    Vd[1] = fma((double)s0, S, Vd[1]); Vd[2] = fma((double)s1, S, Vd[2]); Vd[3] = fma((double)s2, S, Vd[3]);
+  __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI], double (&Vd)[4][ND]) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      if (cmask & (1u << c)) {
+        uint32_t w = quad_get(r.y, c) - ysub;
+        uint32_t g0 = w & 255u, g1 = (w >> 8) & 255u, g2 = (w >> 16) & 255u, yj = w >> 24;
+        double S = __ldg(stab + ((g0 << 8) | yj));
+        if (SIGN > 0) {
+          if (!(S == S)) nanf = 1u;
+          Vi[c][0] += g0; Vi[c][1] += g1; Vi[c][2] += g2;
+          Vi[c][3] += g0 * g0; Vi[c][4] += g0 * g1; Vi[c][5] += g0 * g2;
+          Vi[c][6] += g1 * g1; Vi[c][7] += g1 * g2; Vi[c][8] += g2 * g2;
+        } else {
+          S = -S;
+          Vi[c][0] -= g0; Vi[c][1] -= g1; Vi[c][2] -= g2;
+          Vi[c][3] -= g0 * g0; Vi[c][4] -= g0 * g1; Vi[c][5] -= g0 * g2;
+          Vi[c][6] -= g1 * g1; Vi[c][7] -= g1 * g2; Vi[c][8] -= g2 * g2;
+        }
+        Vd[c][0] += S;
+        Vd[c][1] = fma(u2d(g0), S, Vd[c][1]); Vd[c][2] = fma(u2d(g1), S, Vd[c][2]); Vd[c][3] = fma(u2d(g2), S, Vd[c][3]);
+      }
+    }
   }
-  __device__ __forceinline__ void epilogue(int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
-    double N = (double)Ncnt, invN = 1.0 / N;
+  __device__ __forceinline__ void row_begin(int, int) {}
+  __device__ __forceinline__ void column(int cc, int, int, int Ncnt, const uint32_t* si, const double* sd) {
+    double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
     double M[6], Sd[3], A[6], rdet, a[3], b;
     gf_build_M(si, N, epsN_k * N * N, M, Sd);
     gf_adjugate(M, A, rdet);
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 1, a, b);
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-    ab[0 * n_px + pix] = (float)a[0]; ab[1 * n_px + pix] = (float)a[1]; ab[2 * n_px + pix] = (float)a[2]; ab[3 * n_px + pix] = (float)b;
+    o[cc][0] = (float)a[0]; o[cc][1] = (float)a[1]; o[cc][2] = (float)a[2]; o[cc][3] = (float)b;
+  }
+  __device__ __forceinline__ void store_pair(int y, int x) {
+    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<float2*>(ab + k * n_pp + pp) = make_float2(o[0][k], o[1][k]);
   }
   __device__ void finish() {
     unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
@@ -608,197 +715,379 @@ struct PolGF2a {
 
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
-  static constexpr int NI = 0, ND = 4;
+  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 192;
+  static constexpr bool PREFETCH = false;
   typedef ExpShared Shared;
-  GfCommon g; Shared* sh; int W, H, f;
-  const uint8_t* img; const float* J; const float* ab; float* refS;
-  unsigned long long omn, omx; unsigned nanf;
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, int W_, int H_) {
-    g = gc; sh = s; W = W_; H = H_; f = frame;
-    size_t n_px = (size_t)W * H;
-    img = g.src + (size_t)f * n_px * 3;
-    J = g.J + (size_t)f * 2 * n_px;
-    ab = g.ab + (size_t)f * 8 * n_px;
-    refS = g.refS + (size_t)f * n_px;
-    exp_shared_init(sh, g.fs[f], (double)n_px);
-    omn = ~0ull; omx = 0; nanf = 0;
+  struct Raw {};
+  GfCommon g; Shared* sh; int Wp, H, f;
+  const uint32_t* kq; const uint32_t* ycc; const float* J; const float* ab; float* refS;
+  double omn, omx; unsigned nanf;
+  uint4 krow, yrow; float4 jb, jg;
+  float o[2];
+  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
+    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
+    size_t n_pp = (size_t)Wp * H;
+    kq = g.kq + (size_t)f * n_pp;
+    ycc = g.ycc + (size_t)f * n_pp;
+    J = g.J + (size_t)f * 2 * n_pp;
+    ab = g.ab + (size_t)f * 8 * n_pp;
+    refS = g.refS + (size_t)f * n_pp;
+    exp_shared_init(sh, g.fs[f], (double)gg.W * (double)gg.H);
+    omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
   }
-  template <int SIGN>
-  __device__ __forceinline__ void accum(int y, int x, uint32_t*, double* Vd) const {
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      double v = (double)__ldg(ab + k * n_px + pix);
-      Vd[k] += (SIGN > 0 ? v : -v);
-    }
+  __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
+    gf_accum_planes<4>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
   }
-  __device__ __forceinline__ void epilogue(int y, int x, int Ncnt, const uint32_t*, const double* sd) {
-    double invN = 1.0 / (double)Ncnt;
-    size_t n_px = (size_t)W * H, pix = (size_t)y * W + x;
-    PixelExp e;
-    eval_pixel(sh, img + pix * 3, __ldg(J + pix), __ldg(J + n_px + pix), e);
-    double q = (sd[0] * (double)e.gy + sd[1] * (double)e.gcr + sd[2] * (double)e.gcb + sd[3]) * invN;
+  __device__ __forceinline__ void row_begin(int y, int gx) {
+    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
+    krow = __ldg(reinterpret_cast<const uint4*>(kq + o));
+    yrow = __ldg(reinterpret_cast<const uint4*>(ycc + o));
+    jb = __ldg(reinterpret_cast<const float4*>(J + o));
+    jg = __ldg(reinterpret_cast<const float4*>(J + n_pp + o));
+  }
+  __device__ __forceinline__ void column(int cc, int, int x, int Ncnt, const uint32_t*, const double* sd) {
+    double invN = rcp_fast(u2d((uint32_t)Ncnt));
+    int c4 = x & 3;
+    uint32_t yw = quad_get(yrow, c4);
+    uint32_t ymin = (uint32_t)sh->fc.yi_min;
+    double g0 = u2d((yw & 255u) - ymin), g1 = u2d(((yw >> 8) & 255u) - ymin), g2 = u2d(((yw >> 16) & 255u) - ymin);
+    double q = (sd[0] * g0 + sd[1] * g1 + sd[2] * g2 + sd[3]) * invN;
     float qf = (float)q;
-    refS[pix] = qf;
+    o[cc] = qf;
     double qr = (double)qf;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      double o = e.rest[c] * qr;
-      if (!(o == o)) { nanf = 1u; o = 0.0; }
-      unsigned long long key = dkey(o);
-      omn = key < omn ? key : omn;
-      omx = key > omx ? key : omx;
+    double rb = norm_j_fast(quad_get(jb, c4), sh->fc, 0), rg = norm_j_fast(quad_get(jg, c4), sh->fc, 1);
+    double rr = sh->rt.redN[(quad_get(krow, c4) >> 16) & 255u];
+    // min / max over the three channels of restored * refinedS
+    double o0 = rb * qr, o1 = rg * qr, o2 = rr * qr;
+    if (!(o0 == o0) || !(o1 == o1) || !(o2 == o2)) { nanf = 1u; }
+    else {
+      omn = fmin(omn, fmin(o0, fmin(o1, o2)));
+      omx = fmax(omx, fmax(o0, fmax(o1, o2)));
     }
+  }
+  __device__ __forceinline__ void store_pair(int y, int x) {
+    *reinterpret_cast<float2*>(refS + (size_t)y * Wp + x) = make_float2(o[0], o[1]);
   }
   __device__ void finish() {
-    unsigned long long a = warp_min_u64(omn), b = warp_max_u64(omx);
+    double a = warp_min_f64(omn), b = warp_max_f64(omx);
     unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
     if ((threadIdx.x & 31) == 0) {
-      atomicMin(&g.fs[f].omin_key, a);
-      atomicMax(&g.fs[f].omax_key, b);
+      if (a <= b) {
+        atomicMin(&g.fs[f].omin_key, dkey(a));
+        atomicMax(&g.fs[f].omax_key, dkey(b));
+      }
       if (nf) atomicOr(&g.fs[f].nan_flag, 1u);
     }
   }
 };
 
 // -------------------------------------------------------------------------------------------------
-// the march kernel
+// the quad-march kernel
 // -------------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ void gf_phase1(T* arr, int g16, unsigned hmask) {
-  // serial inclusive prefix over this segment's GF_SEG columns, then add the exclusive scan of the
-  // 16 segment totals (half-warp shuffle scan) so that arr[] holds the prefix over the whole strip.
+// One scan task: SEGQ consecutive quad totals of one moment -> inclusive prefix over the whole row.
+// The eight tasks of a moment sit in eight adjacent lanes; their segment totals are exchanged with
+// shuffles.  Every lane of the warp takes part (lanes without a task carry zeros).
+template <class T, class V4>
+__device__ __forceinline__ void gf_scan_task(T* row, int seg, int SEGQ, bool live) {
+  constexpr int VW = sizeof(V4) / sizeof(T);  // 4 (u32) or 2 (f64)
+  T* p = row + seg * SEGQ;
   T tot = 0;
-#pragma unroll
-  for (int i = 0; i < GF_SEG; i++) tot += arr[i * (GF_NSEG + 1) + g16];
+  if (live) {
+    for (int i = 0; i < SEGQ; i += VW) {
+      V4 v = *reinterpret_cast<const V4*>(p + i);
+      if constexpr (VW == 4) tot += (v.x + v.y) + (v.z + v.w); else tot += v.x + v.y;
+    }
+  }
   T incl = tot;
 #pragma unroll
-  for (int d = 1; d < 16; d <<= 1) {
-    T o = __shfl_up_sync(hmask, incl, d, 16);
-    if (g16 >= d) incl += o;
+  for (int d = 1; d < GF_NSEG; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, incl, d, GF_NSEG);
+    if (seg >= d) incl += o;
   }
-  T run = incl - tot;
-#pragma unroll
-  for (int i = 0; i < GF_SEG; i++) {
-    run += arr[i * (GF_NSEG + 1) + g16];
-    arr[i * (GF_NSEG + 1) + g16] = run;
+  T run = __shfl_up_sync(0xffffffffu, incl, 1, GF_NSEG);  // exclusive offset (never derived from this segment's own total)
+  if (seg == 0) run = 0;
+  if (live) {
+    for (int i = 0; i < SEGQ; i += VW) {
+      V4 v = *reinterpret_cast<const V4*>(p + i);
+      if constexpr (VW == 4) { v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w; }
+      else { v.x += run; v.y += v.x; run = v.y; }
+      *reinterpret_cast<V4*>(p + i) = v;
+    }
   }
 }
 
 template <class P>
-__global__ void __launch_bounds__(GF_NT, 2) gf_march_kernel(GfCommon gc, int W, int H, int r, int seg_h) {
-  constexpr int NI = P::NI, ND = P::ND, NQ = NI + ND;
+__global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
+  constexpr int NI = P::NI, ND = P::ND;
+  constexpr int NIa = NI > 0 ? NI : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_d = reinterpret_cast<double*>(smem_raw);                       // [ND][GF_PITCH]
-  uint32_t* s_i = reinterpret_cast<uint32_t*>(s_d + ND * GF_PITCH);        // [NI][GF_PITCH]
-  typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(smem_raw + (((size_t)ND * GF_PITCH * 8 + (size_t)NI * GF_PITCH * 4 + 15) & ~(size_t)15));
+  const int NQ = gg.NQ, PW = NQ * 4, GP = gg.GP;
+  // layout: Pd [ND][PW] f64 | Gd [ND][GP] f64 | Pi [NI][PW] u32 | Gi [NI][GP] u32 | policy tables
+  double* Pd = reinterpret_cast<double*>(smem_raw);
+  double* Gd = Pd + (size_t)ND * PW;
+  uint32_t* Pi = reinterpret_cast<uint32_t*>(Gd + (size_t)ND * GP);
+  uint32_t* Gi = Pi + (size_t)NI * PW;
+  typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(Gi + (size_t)NI * GP);  // 16-byte aligned: PW, GP are multiples of 4
   P pol;
-  pol.init(gc, blockIdx.z, sh, W, H);
+  pol.init(gc, blockIdx.z, sh, gg);
 
   const int t = threadIdx.x;
-  const int SW = GF_NT - 2 * r;
-  const int xs = blockIdx.x * SW;
-  const int x = xs - r + t;
-  const bool xin = (x >= 0 && x < W);
-  const int ys = blockIdx.y * seg_h, ye = min(ys + seg_h, H);
-  const bool is_out = (t >= r) && (t < GF_NT - r) && (x < W);
-  const int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
-  const int my_slot = (t % GF_SEG) * (GF_NSEG + 1) + t / GF_SEG;
-  const int hi_c = t + r, lo_c = t - r - 1;
-  const int hi_slot = (hi_c % GF_SEG) * (GF_NSEG + 1) + hi_c / GF_SEG;
-  const int lo_slot = lo_c >= 0 ? (lo_c % GF_SEG) * (GF_NSEG + 1) + lo_c / GF_SEG : 0;
+  const int W = gg.W, H = gg.H, r = gg.r;
+  const int xs = blockIdx.x * gg.SW;
+  const int gx = xs - gg.HL - 4 + 4 * t;      // image column of this thread's quad (multiple of 4)
+  const bool qact = t < NQ;
+  unsigned cmask = 0;                         // columns of the quad that are image columns; quad 0 is the zero guard
+  if (qact && t > 0) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) if (gx + c >= 0 && gx + c < W) cmask |= 1u << c;
+  }
+  const bool qload = cmask != 0;              // then 0 <= gx < Wp: the whole quad is readable
+  const int ys = blockIdx.y * gg.seg_h, ye = min(ys + gg.seg_h, H);
+  const int y_first = max(ys - r, 0);         // first row that enters the running sums
+  // output quads of this strip
+  const int tq0 = gg.HL / 4 + 1;
+  const bool oact = (t >= tq0) && (t < tq0 + gg.SW / 4) && (gx < W);
+  const int rho = r >> 2;
 
-  uint32_t Vi[NI > 0 ? NI : 1];
-  double Vd[ND > 0 ? ND : 1];
+  uint32_t Vi[4][NIa];
+  double Vd[4][ND];
 #pragma unroll
-  for (int k = 0; k < NI; k++) Vi[k] = 0;
+  for (int c = 0; c < 4; c++) {
 #pragma unroll
-  for (int k = 0; k < ND; k++) Vd[k] = 0.0;
+    for (int k = 0; k < NIa; k++) Vi[c][k] = 0;
+#pragma unroll
+    for (int k = 0; k < ND; k++) Vd[c][k] = 0.0;
+  }
+
+  typename P::Raw curE, curL;
+  if constexpr (P::PREFETCH) {
+    pol.zero(curE); pol.zero(curL);
+    int yin = ys - r, yl = yin - 2 * r - 1;
+    if (qload && yin >= 0 && yin < H) pol.load(yin, gx, curE);
+    if (qload && yl >= y_first) pol.load(yl, gx, curL);
+  }
 
   for (int yin = ys - r; yin < ye + r; ++yin) {
-    if (xin) {
-      if (yin >= 0 && yin < H) pol.template accum<+1>(yin, x, Vi, Vd);
-      int yl = yin - 2 * r - 1;
-      if (yl >= ys - r && yl >= 0) pol.template accum<-1>(yl, x, Vi, Vd);
+    const int yl = yin - 2 * r - 1;
+    const bool enter = (yin >= 0 && yin < H), leave = (yl >= y_first);
+    if constexpr (P::PREFETCH) {
+      typename P::Raw nxE, nxL;
+      pol.zero(nxE); pol.zero(nxL);
+      const int yn = yin + 1, yln = yl + 1;
+      if (qload && yn < ye + r) {
+        if (yn >= 0 && yn < H) pol.load(yn, gx, nxE);
+        if (yln >= y_first) pol.load(yln, gx, nxL);
+      }
+      if (qload) {
+        if (enter) pol.template accum<+1>(curE, cmask, Vi, Vd);
+        if (leave) pol.template accum<-1>(curL, cmask, Vi, Vd);
+      }
+      curE = nxE; curL = nxL;
+    } else {
+      if (qload && (enter || leave)) pol.accum_direct(yin, enter, yl, leave, gx, cmask, Vd);
     }
-    int yo = yin - r;
+    const int yo = yin - r;
     if (yo < ys) continue;  // warm-up rows (uniform across the CTA)
+
+    // ---- publish the quad prefixes and totals -------------------------------------------------------
+    for (int i = NQ + t; i < GP; i += P::NT) {  // tail of the quad-total rows: keep it finite
 #pragma unroll
-    for (int k = 0; k < NI; k++) s_i[k * GF_PITCH + my_slot] = Vi[k];
+      for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
 #pragma unroll
-    for (int k = 0; k < ND; k++) s_d[k * GF_PITCH + my_slot] = Vd[k];
-    __syncthreads();
-    if (t < NQ * 16) {
-      int q = t >> 4, g16 = t & 15;
-      unsigned hmask = 0xffffu << (t & 16);  // the two half-warps scan different quantities
-      if (q < NI) gf_phase1<uint32_t>(s_i + q * GF_PITCH, g16, hmask);
-      else gf_phase1<double>(s_d + (q - NI) * GF_PITCH, g16, hmask);
+      for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
+    }
+    if (qact) {
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+        uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+        *reinterpret_cast<uint4*>(Pi + (size_t)k * PW + 4 * t) = make_uint4(p0, p1, p2, p3);
+        Gi[k * GP + t] = p3;
+      }
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+        double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+        double2* d = reinterpret_cast<double2*>(Pd + (size_t)k * PW + 4 * t);
+        d[0] = make_double2(p0, p1);
+        d[1] = make_double2(p2, p3);
+        Gd[k * GP + t] = p3;
+      }
     }
     __syncthreads();
-    if (is_out) {
-      uint32_t si[NI > 0 ? NI : 1];
-      double sd[ND > 0 ? ND : 1];
+    // ---- prefix over the quad totals (warp-aligned task groups: ints first, then doubles) -----------
+    {
+      constexpr int TI = NI * GF_NSEG, TIP = (TI + 31) & ~31, TD = ND * GF_NSEG;
+      if (t < TIP) {
+        if (NI > 0) gf_scan_task<uint32_t, uint4>(Gi + (size_t)min(t >> 3, NIa - 1) * GP, t & 7, gg.SEGQ, t < TI);
+      } else if (t < TIP + ((TD + 31) & ~31)) {
+        int td = t - TIP;
+        gf_scan_task<double, double2>(Gd + (size_t)min(td >> 3, ND - 1) * GP, td & 7, gg.SEGQ, td < TD);
+      }
+    }
+    __syncthreads();
+    // ---- window sums and the per-pixel work -----------------------------------------------------------
+    if (oact) {
+      const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
+      pol.row_begin(yo, gx);
+      uint32_t si[4][NIa];
+      if (gg.fast) {
 #pragma unroll
-      for (int k = 0; k < NI; k++) si[k] = s_i[k * GF_PITCH + hi_slot] - (lo_c >= 0 ? s_i[k * GF_PITCH + lo_slot] : 0u);
+        for (int k = 0; k < NI; k++) {
+          uint32_t Wq = Gi[k * GP + t + rho - 1] - Gi[k * GP + t - rho - 1];
+          uint4 a = *reinterpret_cast<const uint4*>(Pi + (size_t)k * PW + 4 * (t - rho));
+          uint4 b = *reinterpret_cast<const uint4*>(Pi + (size_t)k * PW + 4 * (t + rho));
+          si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < ND; k++) sd[k] = s_d[k * GF_PITCH + hi_slot] - (lo_c >= 0 ? s_d[k * GF_PITCH + lo_slot] : 0.0);
-      int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
-      pol.epilogue(yo, x, ny * nx, si, sd);
+        for (int c = 0; c < 4; c++) {
+          int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+#pragma unroll
+          for (int k = 0; k < NI; k++) {
+            uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pi[(size_t)k * PW + zl - 1] : 0u);
+            uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pi[(size_t)k * PW + zh - 1] : 0u);
+            si[c][k] = fh - fl;
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        double sd[2][ND];
+        if (gg.fast) {
+#pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double Wq = Gd[k * GP + t + rho - 1] - Gd[k * GP + t - rho - 1];
+            const double* pa = Pd + (size_t)k * PW + 4 * (t - rho);
+            double2 b = *reinterpret_cast<const double2*>(Pd + (size_t)k * PW + 4 * (t + rho) + 2 * h);
+            if (h == 0) {
+              double a0 = pa[0];
+              sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a0) + b.y;
+            } else {
+              double a1 = pa[1], a2 = pa[2];
+              sd[0][k] = (Wq - a1) + b.x; sd[1][k] = (Wq - a2) + b.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) {
+            int c = 2 * h + cc;
+            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+              double fl = Gd[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pd[(size_t)k * PW + zl - 1] : 0.0);
+              double fh = Gd[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pd[(size_t)k * PW + zh - 1] : 0.0);
+              sd[cc][k] = fh - fl;
+            }
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          int x = gx + 2 * h + cc;
+          if (x < W) {
+            int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
+            pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
+          }
+        }
+        if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
+      }
     }
     __syncthreads();
   }
   pol.finish();
 }
 
+// geometry + launch -------------------------------------------------------------------------------------
 template <class P>
-static size_t gf_smem_bytes() {
-  return (((size_t)P::ND * GF_PITCH * 8 + (size_t)P::NI * GF_PITCH * 4 + 15) & ~(size_t)15) + sizeof(typename P::Shared);
+static size_t gf_smem_bytes(const GfGeom& gg) {
+  size_t PW = (size_t)gg.NQ * 4;
+  return (size_t)P::ND * (PW + gg.GP) * 8 + (size_t)P::NI * (PW + gg.GP) * 4 + sizeof(typename P::Shared);
+}
+
+static GfGeom gf_geometry(int W, int H, int r, int NT) {
+  GfGeom g;
+  g.W = W; g.H = H; g.Wp = (W + 3) & ~3; g.r = r;
+  g.HL = (r + 3) & ~3;
+  int sw_max = 4 * (NT - 1) - 2 * g.HL;
+  int strips = cdiv(W, sw_max);
+  g.SW = (cdiv(W, strips) + 3) & ~3;
+  g.NQ = 1 + (2 * g.HL + g.SW) / 4;
+  int s4 = cdiv(g.NQ, 4 * GF_NSEG);
+  if ((s4 & 1) == 0) s4++;            // odd number of 16-byte chunks per segment: conflict-free vector loads
+  g.SEGQ = 4 * s4;
+  g.GP = GF_NSEG * g.SEGQ;
+  g.seg_h = H;
+  g.fast = (r % 4 == 0) ? 1 : 0;
+  return g;
 }
 
 template <class P>
 static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, int W, int H, int r) {
-  int SW = GF_NT - 2 * r;
-  int strips = cdiv(W, SW);
-  // split rows into segments until there are ~2 waves of CTAs (2 CTAs per SM resident)
-  int target = ctx->sm_count * 4;
-  int segs = cdiv(target, strips * n);
-  int max_segs = H / (4 * r + 2) > 1 ? H / (4 * r + 2) : 1;  // keep the 2r warm-up rows below ~1/3 of the work
-  if (segs > max_segs) segs = max_segs;
-  if (segs < 1) segs = 1;
-  int seg_h = cdiv(H, segs);
-  segs = cdiv(H, seg_h);
-  size_t smem = gf_smem_bytes<P>();
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
+  GfGeom gg = gf_geometry(W, H, r, P::NT);
+  int strips = cdiv(W, gg.SW);
+  // vertical segments: fill the machine (tail of the last wave) against the 2r warm-up rows per segment
+  int slots = ctx->sm_count * P::MINB;
+  int tasks = strips * n;
+  int best = 1;
+  double best_eff = 0.0;
+  int max_segs = std::max(1, H / (4 * r + 2));
+  for (int s = 1; s <= max_segs && s <= 64; s++) {
+    int sh = cdiv(H, s), sc = cdiv(H, sh);
+    double waves = (double)cdiv(tasks * sc, slots);
+    double eff = ((double)tasks * sc / (waves * slots)) * ((double)sh / (double)(sh + 2 * r));
+    if (eff > best_eff * 1.02) { best_eff = eff; best = s; }
+  }
+  gg.seg_h = cdiv(H, best);
+  int segs = cdiv(H, gg.seg_h);
+  size_t smem = gf_smem_bytes<P>(gg);
+  static size_t attr = 0;  // per template instantiation
+  if (smem > attr) {
     UWIP_CUDA(ctx, cudaFuncSetAttribute(gf_march_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr = smem;
   }
   dim3 grid(strips, segs, n);
-  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, GF_NT, smem, gc, W, H, r, seg_h);
+  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT, smem, gc, gg);
   return UWIP_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
-// E: restored -> R8, I8 -> YCrCb joint min / max (BGDehaze.py:75-80)
+// E: restored -> R8, I8 -> YCrCb joint min / max (BGDehaze.py:75-80); stores (Yi, Cri, Cbi, Yj)
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) exposure_minmax_kernel(GfCommon g, int W, int H, double* dbg_restored) {
+__global__ void __launch_bounds__(256) exposure_minmax_kernel(GfCommon g, int W, int H, int Wp, double* dbg_restored) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
-  size_t n_px = (size_t)W * H;
-  exp_shared_init(&sh, g.fs[f], (double)n_px);
-  const uint8_t* img = g.src + (size_t)f * n_px * 3;
-  const float* J = g.J + (size_t)f * 2 * n_px;
+  size_t n_pp = (size_t)Wp * H;
+  exp_shared_init(&sh, g.fs[f], (double)W * (double)H);
+  const uint32_t* kq = g.kq + (size_t)f * n_pp;
+  const float* J = g.J + (size_t)f * 2 * n_pp;
+  uint32_t* ycc = g.ycc + (size_t)f * n_pp;
   unsigned imn = 255, imx = 0, jmn = 255, jmx = 0;
-  for (size_t pix = (size_t)blockIdx.x * 256 + threadIdx.x; pix < n_px; pix += (size_t)gridDim.x * 256) {
-    double rest[3];
-    int r8[3], i8[3];
-    restored_pixel(&sh, img + pix * 3, __ldg(J + pix), __ldg(J + n_px + pix), rest, r8, i8);
-    if (dbg_restored && f == 0) { dbg_restored[pix * 3] = rest[0]; dbg_restored[pix * 3 + 1] = rest[1]; dbg_restored[pix * 3 + 2] = rest[2]; }
-    int Y, Cr, Cb;
-    bgr2ycrcb_u8(i8[0], i8[1], i8[2], Y, Cr, Cb);
-    imn = min(imn, (unsigned)imin3(Y, Cr, Cb)); imx = max(imx, (unsigned)imax3(Y, Cr, Cb));
-    bgr2ycrcb_u8(r8[0], r8[1], r8[2], Y, Cr, Cb);
-    jmn = min(jmn, (unsigned)imin3(Y, Cr, Cb)); jmx = max(jmx, (unsigned)imax3(Y, Cr, Cb));
+  const int qpr = Wp / 4;
+  const size_t n_q = (size_t)qpr * H;
+  for (size_t qi = (size_t)blockIdx.x * 256 + threadIdx.x; qi < n_q; qi += (size_t)gridDim.x * 256) {
+    int y = (int)(qi / qpr), x0 = (int)(qi - (size_t)y * qpr) * 4;
+    size_t pp = (size_t)y * Wp + x0;
+    uint4 kw = __ldg(reinterpret_cast<const uint4*>(kq + pp));
+    float4 jb = __ldg(reinterpret_cast<const float4*>(J + pp)), jg = __ldg(reinterpret_cast<const float4*>(J + n_pp + pp));
+    uint32_t out[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      out[c] = 0;
+      if (x0 + c >= W) continue;
+      uint32_t w = quad_get(kw, c);
+      uint32_t kb = w & 255u, kg = (w >> 8) & 255u, kr = (w >> 16) & 255u;
+      double rb = norm_j(quad_get(jb, c), sh.fc, 0), rg = norm_j(quad_get(jg, c), sh.fc, 1);
+      if (dbg_restored && f == 0) {
+        size_t pix = (size_t)y * W + x0 + c;
+        dbg_restored[pix * 3] = rb; dbg_restored[pix * 3 + 1] = rg; dbg_restored[pix * 3 + 2] = sh.rt.redN[kr];
+      }
+      int r8b = trunc_u8(rb * 255.0), r8g = trunc_u8(rg * 255.0), r8r = sh.rt.red8[kr];
+      int Yi, Cri, Cbi, Yj, Crj, Cbj;
+      bgr2ycrcb_u8(sh.rt.i8[kb], sh.rt.i8[kg], sh.rt.i8[kr], Yi, Cri, Cbi);
+      imn = min(imn, (unsigned)imin3(Yi, Cri, Cbi)); imx = max(imx, (unsigned)imax3(Yi, Cri, Cbi));
+      bgr2ycrcb_u8(r8b, r8g, r8r, Yj, Crj, Cbj);
+      jmn = min(jmn, (unsigned)imin3(Yj, Crj, Cbj)); jmx = max(jmx, (unsigned)imax3(Yj, Crj, Cbj));
+      out[c] = (uint32_t)Yi | ((uint32_t)Cri << 8) | ((uint32_t)Cbi << 16) | ((uint32_t)Yj << 24);
+    }
+    *reinterpret_cast<uint4*>(ycc + pp) = make_uint4(out[0], out[1], out[2], out[3]);
   }
   imn = warp_reduce_min_u32(imn); imx = warp_reduce_max_u32(imx);
   jmn = warp_reduce_min_u32(jmn); jmx = warp_reduce_max_u32(jmx);
@@ -809,34 +1098,65 @@ __global__ void __launch_bounds__(256) exposure_minmax_kernel(GfCommon g, int W,
   }
 }
 
+// S (BGDehaze.py:83) as a table over (Yi - min, Yj - min): both are bytes.  grid (256, n), block 256.
+__global__ void __launch_bounds__(256) stab_kernel(const FrameState* __restrict__ fs, double* __restrict__ stab) {
+  int f = blockIdx.y, gy = blockIdx.x, j = threadIdx.x;
+  const FrameState& s = fs[f];
+  double yi_rng = (double)((int)s.yi_max - (int)s.yi_min), yj_rng = (double)((int)s.yj_max - (int)s.yj_min);
+  double yi = (double)gy / yi_rng, yj = (double)j / yj_rng;
+  double yi2 = 0.3 * (yi * yi);
+  stab[(size_t)f * 65536 + gy * 256 + j] = (yj * yi + yi2) / (yj * yj + yi2);
+}
+
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
-__global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
-  size_t n_px = (size_t)W * H;
-  exp_shared_init(&sh, g.fs[f], (double)n_px);
+  size_t n_pp = (size_t)Wp * H;
+  exp_shared_init(&sh, g.fs[f], (double)W * (double)H);
   const FrameState& s = g.fs[f];
   double omn = dunkey(s.omin_key), den = dunkey(s.omax_key) - omn;
+  double scale = 255.0 / den;
   bool nan_frame = s.nan_flag != 0;
   if (flags && blockIdx.x == 0 && threadIdx.x == 0) flags[f] = nan_frame ? UWIP_FRAME_NAN : 0;
-  const uint8_t* img = g.src + (size_t)f * n_px * 3;
-  const float* J = g.J + (size_t)f * 2 * n_px;
-  const float* refS = g.refS + (size_t)f * n_px;
-  uint8_t* out = dst + (size_t)f * n_px * 3;
-  for (size_t pix = (size_t)blockIdx.x * 256 + threadIdx.x; pix < n_px; pix += (size_t)gridDim.x * 256) {
-    double rest[3];
-    int r8[3], i8[3];
-    restored_pixel(&sh, img + pix * 3, __ldg(J + pix), __ldg(J + n_px + pix), rest, r8, i8);
-    double q = (double)__ldg(refS + pix);
+  const uint32_t* kq = g.kq + (size_t)f * n_pp;
+  const float* J = g.J + (size_t)f * 2 * n_pp;
+  const float* refS = g.refS + (size_t)f * n_pp;
+  uint8_t* out = dst + (size_t)f * W * H * 3;
+  const int qpr = Wp / 4;
+  const size_t n_q = (size_t)qpr * H;
+  const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+  for (size_t qi = (size_t)blockIdx.x * 256 + threadIdx.x; qi < n_q; qi += (size_t)gridDim.x * 256) {
+    int y = (int)(qi / qpr), x0 = (int)(qi - (size_t)y * qpr) * 4;
+    size_t pp = (size_t)y * Wp + x0;
+    uint4 kw = __ldg(reinterpret_cast<const uint4*>(kq + pp));
+    float4 jb = __ldg(reinterpret_cast<const float4*>(J + pp)), jg = __ldg(reinterpret_cast<const float4*>(J + n_pp + pp));
+    float4 qs = __ldg(reinterpret_cast<const float4*>(refS + pp));
+    uint8_t b[12];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      double o = (rest[c] * q - omn) / den;
-      if (nan_frame) o = __longlong_as_double(0x7ff8000000000000ll);
-      if (dbg_out && f == 0) dbg_out[pix * 3 + c] = o;
-      double v = o * 255.0;
-      int b = 0;
-      if (v == v && fabs(v) < 2.0e9) b = min(max(__double2int_rn(v), 0), 255);
-      out[pix * 3 + c] = (uint8_t)b;
+    for (int c = 0; c < 4; c++) {
+      double rest[3];
+      rest[0] = norm_j_fast(quad_get(jb, c), sh.fc, 0);
+      rest[1] = norm_j_fast(quad_get(jg, c), sh.fc, 1);
+      rest[2] = sh.rt.redN[(quad_get(kw, c) >> 16) & 255u];
+      double q = (double)quad_get(qs, c);
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        double v = (rest[ch] * q - omn) * scale;
+        if (dbg_out && f == 0 && x0 + c < W) dbg_out[((size_t)y * W + x0 + c) * 3 + ch] = nan_frame ? __longlong_as_double(0x7ff8000000000000ll) : (rest[ch] * q - omn) / den;
+        int bv = 0;
+        if (!nan_frame && v == v && fabs(v) < 2.0e9) bv = min(max(__double2int_rn(v), 0), 255);
+        b[c * 3 + ch] = (uint8_t)bv;
+      }
+    }
+    uint8_t* o = out + ((size_t)y * W + x0) * 3;
+    if (vec_ok) {
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+      o32[0] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+      o32[1] = (uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24);
+      o32[2] = (uint32_t)b[8] | ((uint32_t)b[9] << 8) | ((uint32_t)b[10] << 16) | ((uint32_t)b[11] << 24);
+    } else {
+      for (int c = 0; c < 4 && x0 + c < W; c++) { o[c * 3] = b[c * 3]; o[c * 3 + 1] = b[c * 3 + 1]; o[c * 3 + 2] = b[c * 3 + 2]; }
     }
   }
 }
@@ -848,24 +1168,29 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
                       bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags) {
   UWIP_REQUIRE(ctx, n >= 1 && W >= 1 && H >= 1, "bad size");
   UWIP_REQUIRE(ctx, p.window >= 1 && p.window <= WK_MAXWIN, "window must be 1..33");
-  UWIP_REQUIRE(ctx, p.radius >= 1 && 2 * p.radius <= GF_NT - 64, "radius must be 1..160");
+  UWIP_REQUIRE(ctx, p.radius >= 1 && p.radius <= 160, "radius must be 1..160");
   UWIP_REQUIRE(ctx, (size_t)W * H < (1ull << 31), "frame too large");
   UWIP_REQUIRE(ctx, !dbg || n == 1, "stage outputs are single-frame");
   size_t n_px = (size_t)W * H;
+  const int Wp = (W + 3) & ~3;
+  size_t n_pp = (size_t)Wp * H;
   if (!minmax_done) {
     int want = (int)std::min<size_t>((n_px * 3 / 16 + 255) / 256, 1u << 16);
     int gxm = std::max(1, std::min(want, ctx->sm_count * 8 / n + 1));
     dim3 grid(gxm, n);
     UWIP_LAUNCH(ctx, "dz_minmax", minmax_kernel, grid, 256, 0, d_src, n_px * 3, fs);
   }
-  uint8_t* d_m = (uint8_t*)uwip_slot(ctx, SLOT_MPLANES, (size_t)n * 2 * n_px);
-  dim3 gridw(cdiv(W, WK_TX), cdiv(H, WK_TY), n);
+  uint32_t* d_kq = (uint32_t*)uwip_slot(ctx, SLOT_KQ, (size_t)n * n_pp * 4);
+  uint8_t* d_mg = (uint8_t*)uwip_slot(ctx, SLOT_MPLANES, (size_t)n * n_pp);
+  uint32_t* d_ycc = (uint32_t*)uwip_slot(ctx, SLOT_YCC, (size_t)n * n_pp * 4);
+  double* d_stab = (double*)uwip_slot(ctx, SLOT_STAB, (size_t)n * 65536 * 8);
+  dim3 gridw(cdiv(Wp, WK_TX), cdiv(H, WK_TY), n);
   int n_part = gridw.x * gridw.y;
   ArgPartial* d_part = (ArgPartial*)uwip_slot(ctx, SLOT_PARTIALS, (size_t)n * n_part * sizeof(ArgPartial));
-  float* d_ab = (float*)uwip_slot(ctx, SLOT_AB, (size_t)n * 8 * n_px * sizeof(float));
-  float* d_J = (float*)uwip_slot(ctx, SLOT_J, (size_t)n * 2 * n_px * sizeof(float));
-  float* d_refS = (float*)uwip_slot(ctx, SLOT_REFS, (size_t)n * n_px * sizeof(float));
-  if (!d_m || !d_part || !d_ab || !d_J || !d_refS) return UWIP_ERR_NOMEM;
+  float* d_ab = (float*)uwip_slot(ctx, SLOT_AB, (size_t)n * 8 * n_pp * sizeof(float));
+  float* d_J = (float*)uwip_slot(ctx, SLOT_J, (size_t)n * 2 * n_pp * sizeof(float));
+  float* d_refS = (float*)uwip_slot(ctx, SLOT_REFS, (size_t)n * n_pp * sizeof(float));
+  if (!d_kq || !d_mg || !d_ycc || !d_stab || !d_part || !d_ab || !d_J || !d_refS) return UWIP_ERR_NOMEM;
   {
     const int wmax = p.window, wmin = WK_TWIN;
     int PL = std::max(wmax / 2, wmin / 2), PR = std::max(wmax - 1 - wmax / 2, wmin - 1 - wmin / 2);
@@ -876,34 +1201,37 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
       UWIP_CUDA(ctx, cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr = smem;
     }
-    UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, wmax, fs, d_m, d_part);
-    UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 1, wmax == WK_TWIN ? 1 : 0);
     if (wmax != WK_TWIN) {
-      // refined_t() is always called without w (BGDehaze.py:52): the transmission uses the
-      // background light of a 15x15 window even when Background_light for J uses another w
-      UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, WK_TWIN, fs, d_m, d_part);
-      UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 0, 1);
+      // Background_light(normI, w) for dehazed_BG's B (BGDehaze.py:51) uses the caller's window ...
+      UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, Wp, wmax, fs, d_kq, d_mg, d_part);
+      UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 1, 0);
     }
+    // ... but refined_t() is always called without w (BGDehaze.py:52): the transmission and the
+    // background light inside transmission_map use the 15x15 window
+    UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, Wp, WK_TWIN, fs, d_kq, d_mg, d_part);
+    UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, wmax == WK_TWIN ? 1 : 0, 1);
   }
   if (dbg && dbg->stop_after == 1) return UWIP_OK;
   if (dbg && dbg->t_raw) {
     dim3 g2(cdiv(W, 256), H);
-    UWIP_LAUNCH(ctx, "dz_traw", traw_kernel, g2, 256, 0, d_m, W, H, fs, dbg->t_raw);
+    UWIP_LAUNCH(ctx, "dz_traw", traw_kernel, g2, 256, 0, d_kq, d_mg, W, H, Wp, fs, dbg->t_raw);
   }
   if (dbg && dbg->stop_after == 2) return UWIP_OK;
 
   GfCommon gc;
-  gc.src = d_src; gc.mplanes = d_m; gc.ab = d_ab; gc.J = d_J; gc.refS = d_refS; gc.fs = fs;
+  gc.kq = d_kq; gc.mg = d_mg; gc.ycc = d_ycc; gc.stab = d_stab; gc.ab = d_ab; gc.J = d_J; gc.refS = d_refS; gc.fs = fs;
   gc.eps = p.eps; gc.tmin = p.tmin; gc.dbg_tref = dbg ? dbg->t_ref : nullptr;
   UWIP_CHECK(gf_launch<PolGF1a>(ctx, "dz_gf1a", gc, n, W, H, p.radius));
   UWIP_CHECK(gf_launch<PolGF1b>(ctx, "dz_gf1b", gc, n, W, H, p.radius));
   if (dbg && dbg->stop_after == 3) return UWIP_OK;
-  int gx = std::max(1, std::min((int)((n_px + 2047) / 2048), std::max(1, ctx->sm_count * 8 / n)));
+  int gx = std::max(1, std::min((int)((n_pp / 4 + 1023) / 1024), std::max(1, ctx->sm_count * 8 / n)));
   dim3 grid_e(gx, n);
-  UWIP_LAUNCH(ctx, "dz_exposure_minmax", exposure_minmax_kernel, grid_e, 256, 0, gc, W, H, dbg ? dbg->restored : (double*)nullptr);
+  UWIP_LAUNCH(ctx, "dz_exposure_minmax", exposure_minmax_kernel, grid_e, 256, 0, gc, W, H, Wp, dbg ? dbg->restored : (double*)nullptr);
   if (dbg && dbg->stop_after == 4) return UWIP_OK;
+  dim3 grid_s(256, n);
+  UWIP_LAUNCH(ctx, "dz_stab", stab_kernel, grid_s, 256, 0, fs, d_stab);
   UWIP_CHECK(gf_launch<PolGF2a>(ctx, "dz_gf2a", gc, n, W, H, p.radius));
   UWIP_CHECK(gf_launch<PolGF2b>(ctx, "dz_gf2b", gc, n, W, H, p.radius));
-  UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, d_dst, dbg ? dbg->out : (double*)nullptr, d_flags);
+  UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, Wp, d_dst, dbg ? dbg->out : (double*)nullptr, d_flags);
   return UWIP_OK;
 }
