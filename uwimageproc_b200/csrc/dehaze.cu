@@ -52,8 +52,8 @@ FrameState* frame_state_get(uwip_ctx* ctx, int n) { return (FrameState*)uwip_slo
 // ------------------------------------------------------------------------------------------------
 // small fp64 helpers
 // ------------------------------------------------------------------------------------------------
-// exact uint32 -> double without the conversion pipe (u < 2^32): 2^52 + u, minus 2^52
-__device__ __forceinline__ double u2d(uint32_t u) { return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0; }
+// exact uint32 -> double: one I2F on the conversion pipe (the 2^52 magic-add form costs three issue slots)
+__device__ __forceinline__ double u2d(uint32_t u) { return __uint2double_rn(u); }
 // 1/x to ~1 ulp (MUFU seed + two Newton steps).  Used where the result feeds continuous arithmetic
 // only; every place whose result is truncated to a byte uses the IEEE division.
 __device__ __forceinline__ double rcp_fast(double x) {
@@ -65,6 +65,19 @@ __device__ __forceinline__ double rcp_fast(double x) {
   r = fma(r, e, r);
   return r;
 }
+
+// cp.async (LDGSTS): global -> shared without a register in between
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 
 // ------------------------------------------------------------------------------------------------
 // D0: joint min / max over all channels (bgdehaze/main.py:17)
@@ -333,7 +346,6 @@ struct GfGeom {
   int HL;         // halo rounded up to a multiple of 4
   int SW;         // output columns per strip (multiple of 4)
   int NQ;         // quads per strip: one zero guard quad + (2*HL + SW)/4
-  int SEGQ, GP;   // quads per scan segment; pitch of the quad-total rows (8*SEGQ >= NQ)
   int seg_h;      // output rows per vertical segment
   int fast;       // r % 4 == 0: window edges fall on quad boundaries
 };
@@ -472,6 +484,8 @@ __device__ __forceinline__ void gf_accum_planes(const float* __restrict__ base, 
 // policies: what is accumulated per pixel (accum), and what is made of the window sums (column)
 // -------------------------------------------------------------------------------------------------
 constexpr int GF_NSEG = 8;    // scan segments per quad-total row
+constexpr int GF_SEGQ = 28;   // quads per segment (7 x 16 bytes: an odd chunk count keeps the vector loads conflict-free)
+constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max threads per CTA
 
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
@@ -485,7 +499,6 @@ struct PolGF1a {
   GfCommon g; Shared* sh; int Wp, H, f;
   const uint32_t* kq; const uint8_t* mg; float* ab;
   double epsN_k;  // eps * range^2
-  float o[2][8];
   __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
     g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
     size_t n_pp = (size_t)Wp * H;
@@ -503,11 +516,16 @@ struct PolGF1a {
     epsN_k = g.eps * range * range;
     __syncthreads();
   }
-  __device__ __forceinline__ void zero(Raw& r) const { r.k = make_uint4(0, 0, 0, 0); r.m = 0; }
-  __device__ __forceinline__ void load(int y, int gx, Raw& r) const {
+  // staging slot s (0..3 = 2 buffers x enter/leave) of this thread: one uint4 + one u32
+  static constexpr int STAGE_BYTES = 4 * NT * 20;
+  __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx) const {
     size_t o = (size_t)y * Wp + gx;
-    r.k = __ldg(reinterpret_cast<const uint4*>(kq + o));
-    r.m = __ldg(reinterpret_cast<const uint32_t*>(mg + o));
+    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 16, kq + o);
+    cp_async4(st + (size_t)4 * NT * 16 + ((size_t)s * NT + threadIdx.x) * 4, mg + o);
+  }
+  __device__ __forceinline__ void stage_read(const unsigned char* st, int s, Raw& r) const {
+    r.k = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 16);
+    r.m = *reinterpret_cast<const uint32_t*>(st + (size_t)4 * NT * 16 + ((size_t)s * NT + threadIdx.x) * 4);
   }
   template <int SIGN>
   __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI > 0 ? NI : 1], double (&Vd)[4][ND]) const {
@@ -536,23 +554,22 @@ struct PolGF1a {
     }
   }
   __device__ __forceinline__ void row_begin(int, int) {}
-  __device__ __forceinline__ void column(int cc, int, int, int Ncnt, const uint32_t* si, const double* sd) {
+  // results go out column by column (4-byte stores): holding a pair back costs 16 registers that the
+  // 17 running sums x 4 columns do not leave
+  __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
     double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
     double M[6], Sd[3], A[6], rdet;
     gf_build_M(si, N, epsN_k * N * N, M, Sd);
     gf_adjugate(M, A, rdet);
     double a[3], b;
+    size_t n_pp = (size_t)Wp * H;
+    float* o = ab + (size_t)y * Wp + x;
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
-    o[cc][0] = (float)a[0]; o[cc][1] = (float)a[1]; o[cc][2] = (float)a[2]; o[cc][3] = (float)b;
+    o[0] = (float)a[0]; o[n_pp] = (float)a[1]; o[2 * n_pp] = (float)a[2]; o[3 * n_pp] = (float)b;
     gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
-    o[cc][4] = (float)a[0]; o[cc][5] = (float)a[1]; o[cc][6] = (float)a[2]; o[cc][7] = (float)b;
+    o[4 * n_pp] = (float)a[0]; o[5 * n_pp] = (float)a[1]; o[6 * n_pp] = (float)a[2]; o[7 * n_pp] = (float)b;
   }
-  // both columns of the pair lie inside the padded pitch (Wp is a multiple of 4)
-  __device__ __forceinline__ void store_pair(int y, int x) {
-    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) *reinterpret_cast<float2*>(ab + k * n_pp + pp) = make_float2(o[0][k], o[1][k]);
-  }
+  __device__ __forceinline__ void store_pair(int, int) {}
   __device__ void finish() {}
 };
 
@@ -586,8 +603,15 @@ struct PolGF1b {
     cnt = 0; rmn = 255; rmx = 0; rsum = 0; nanf = 0;
     __syncthreads();
   }
+  static constexpr int STAGE_BYTES = 0;
   __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
     gf_accum_planes<8>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
+  }
+  // pull the quads of a later row towards L2 (one request per 128-byte line)
+  __device__ __forceinline__ void prefetch_row(int y, int gx) const {
+    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) prefetch_l2(ab + k * n_pp + o);
   }
   __device__ __forceinline__ void row_begin(int y, int gx) { krow = __ldg(reinterpret_cast<const uint4*>(kq + (size_t)y * Wp + gx)); }
   __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd) {
@@ -667,8 +691,13 @@ struct PolGF2a {
     ysub = a | (a << 8) | (a << 16) | (b << 24);
     nanf = 0;
   }
-  __device__ __forceinline__ void zero(Raw& r) const { r.y = make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ void load(int y, int gx, Raw& r) const { r.y = __ldg(reinterpret_cast<const uint4*>(ycc + (size_t)y * Wp + gx)); }
+  static constexpr int STAGE_BYTES = 4 * NT * 16;
+  __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx) const {
+    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 16, ycc + (size_t)y * Wp + gx);
+  }
+  __device__ __forceinline__ void stage_read(const unsigned char* st, int s, Raw& r) const {
+    r.y = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 16);
+  }
   template <int SIGN>
   __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI], double (&Vd)[4][ND]) {
 #pragma unroll
@@ -735,8 +764,14 @@ struct PolGF2b {
     exp_shared_init(sh, g.fs[f], (double)gg.W * (double)gg.H);
     omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
   }
+  static constexpr int STAGE_BYTES = 0;
   __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
     gf_accum_planes<4>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
+  }
+  __device__ __forceinline__ void prefetch_row(int y, int gx) const {
+    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
+#pragma unroll
+    for (int k = 0; k < 4; k++) prefetch_l2(ab + k * n_pp + o);
   }
   __device__ __forceinline__ void row_begin(int y, int gx) {
     size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
@@ -784,16 +819,17 @@ struct PolGF2b {
 // -------------------------------------------------------------------------------------------------
 // the quad-march kernel
 // -------------------------------------------------------------------------------------------------
-// One scan task: SEGQ consecutive quad totals of one moment -> inclusive prefix over the whole row.
+// One scan task: GF_SEGQ consecutive quad totals of one moment -> inclusive prefix over the whole row.
 // The eight tasks of a moment sit in eight adjacent lanes; their segment totals are exchanged with
 // shuffles.  Every lane of the warp takes part (lanes without a task carry zeros).
 template <class T, class V4>
-__device__ __forceinline__ void gf_scan_task(T* row, int seg, int SEGQ, bool live) {
+__device__ __forceinline__ void gf_scan_task(T* row, int seg, bool live) {
   constexpr int VW = sizeof(V4) / sizeof(T);  // 4 (u32) or 2 (f64)
-  T* p = row + seg * SEGQ;
+  T* p = row + seg * GF_SEGQ;
   T tot = 0;
   if (live) {
-    for (int i = 0; i < SEGQ; i += VW) {
+#pragma unroll
+    for (int i = 0; i < GF_SEGQ; i += VW) {
       V4 v = *reinterpret_cast<const V4*>(p + i);
       if constexpr (VW == 4) tot += (v.x + v.y) + (v.z + v.w); else tot += v.x + v.y;
     }
@@ -807,7 +843,8 @@ __device__ __forceinline__ void gf_scan_task(T* row, int seg, int SEGQ, bool liv
   T run = __shfl_up_sync(0xffffffffu, incl, 1, GF_NSEG);  // exclusive offset (never derived from this segment's own total)
   if (seg == 0) run = 0;
   if (live) {
-    for (int i = 0; i < SEGQ; i += VW) {
+#pragma unroll
+    for (int i = 0; i < GF_SEGQ; i += VW) {
       V4 v = *reinterpret_cast<const V4*>(p + i);
       if constexpr (VW == 4) { v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w; }
       else { v.x += run; v.y += v.x; run = v.y; }
@@ -816,22 +853,39 @@ __device__ __forceinline__ void gf_scan_task(T* row, int seg, int SEGQ, bool liv
   }
 }
 
+// shared-memory layout of one published row; every pitch is a compile-time constant so that each
+// access is base register + immediate:
+//   Pd01 [ND][NT] double2 (prefix 0,1 of the quad) | Pd23 [ND][NT] double2 (prefix 2,3)
+//   Gd [ND][GF_GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GF_GP] u32 | policy tables | cp.async staging
+template <class P>
+struct GfSmem {
+  static constexpr int NT = P::NT, NI = P::NI, ND = P::ND;
+  static constexpr size_t off_d23 = (size_t)ND * NT * 16;
+  static constexpr size_t off_gd = off_d23 + (size_t)ND * NT * 16;
+  static constexpr size_t off_pi = off_gd + (size_t)ND * GF_GP * 8;
+  static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
+  static constexpr size_t off_sh = off_gi + (size_t)NI * GF_GP * 4;
+  static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 15) & ~(size_t)15;
+  static constexpr size_t bytes = off_st + P::STAGE_BYTES;
+};
+
 template <class P>
 __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
-  constexpr int NI = P::NI, ND = P::ND;
+  constexpr int NI = P::NI, ND = P::ND, NT = P::NT, GP = GF_GP;
   constexpr int NIa = NI > 0 ? NI : 1;
+  typedef GfSmem<P> L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NQ = gg.NQ, PW = NQ * 4, GP = gg.GP;
-  // layout: Pd [ND][PW] f64 | Gd [ND][GP] f64 | Pi [NI][PW] u32 | Gi [NI][GP] u32 | policy tables
-  double* Pd = reinterpret_cast<double*>(smem_raw);
-  double* Gd = Pd + (size_t)ND * PW;
-  uint32_t* Pi = reinterpret_cast<uint32_t*>(Gd + (size_t)ND * GP);
-  uint32_t* Gi = Pi + (size_t)NI * PW;
-  typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(Gi + (size_t)NI * GP);  // 16-byte aligned: PW, GP are multiples of 4
+  double2* Pd01 = reinterpret_cast<double2*>(smem_raw);
+  double2* Pd23 = reinterpret_cast<double2*>(smem_raw + L::off_d23);
+  double* Gd = reinterpret_cast<double*>(smem_raw + L::off_gd);
+  uint4* Pi = reinterpret_cast<uint4*>(smem_raw + L::off_pi);
+  uint32_t* Gi = reinterpret_cast<uint32_t*>(smem_raw + L::off_gi);
+  typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(smem_raw + L::off_sh);
   P pol;
   pol.init(gc, blockIdx.z, sh, gg);
 
   const int t = threadIdx.x;
+  const int NQ = gg.NQ;
   const int W = gg.W, H = gg.H, r = gg.r;
   const int xs = blockIdx.x * gg.SW;
   const int gx = xs - gg.HL - 4 + 4 * t;      // image column of this thread's quad (multiple of 4)
@@ -848,6 +902,16 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
   const int tq0 = gg.HL / 4 + 1;
   const bool oact = (t >= tq0) && (t < tq0 + gg.SW / 4) && (gx < W);
   const int rho = r >> 2;
+  // addresses used by the window sums: the quads at -rho / +rho and the totals around them
+  const int tlo = oact ? t - rho : 0, thi = oact ? t + rho : 0;
+
+  // the quad-total rows are scanned over their whole length: keep the unused tail finite
+  for (int i = t; i < GP; i += NT) {
+#pragma unroll
+    for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
+#pragma unroll
+    for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
+  }
 
   uint32_t Vi[4][NIa];
   double Vd[4][ND];
@@ -859,149 +923,153 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
     for (int k = 0; k < ND; k++) Vd[c][k] = 0.0;
   }
 
-  typename P::Raw curE, curL;
+  unsigned char* stage = smem_raw + L::off_st;
   if constexpr (P::PREFETCH) {
-    pol.zero(curE); pol.zero(curL);
+    // rows of the first iteration -> staging buffer 0
     int yin = ys - r, yl = yin - 2 * r - 1;
-    if (qload && yin >= 0 && yin < H) pol.load(yin, gx, curE);
-    if (qload && yl >= y_first) pol.load(yl, gx, curL);
+    if (qload && yin >= 0 && yin < H) pol.stage_issue(stage, 0, yin, gx);
+    if (qload && yl >= y_first) pol.stage_issue(stage, 1, yl, gx);
+    cp_async_commit();
   }
 
-  for (int yin = ys - r; yin < ye + r; ++yin) {
+  int buf = 0;
+  for (int yin = ys - r; yin < ye + r; ++yin, buf ^= 1) {
     const int yl = yin - 2 * r - 1;
     const bool enter = (yin >= 0 && yin < H), leave = (yl >= y_first);
     if constexpr (P::PREFETCH) {
-      typename P::Raw nxE, nxL;
-      pol.zero(nxE); pol.zero(nxL);
+      // this iteration's rows were requested one iteration ago; the next iteration's go out now and
+      // stay in flight (no registers held) until the top of the next iteration
+      cp_async_wait_all();
+      typename P::Raw curE, curL;
+      if (qload && enter) pol.stage_read(stage, 2 * buf, curE);
+      if (qload && leave) pol.stage_read(stage, 2 * buf + 1, curL);
       const int yn = yin + 1, yln = yl + 1;
       if (qload && yn < ye + r) {
-        if (yn >= 0 && yn < H) pol.load(yn, gx, nxE);
-        if (yln >= y_first) pol.load(yln, gx, nxL);
+        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (buf ^ 1), yn, gx);
+        if (yln >= y_first) pol.stage_issue(stage, 2 * (buf ^ 1) + 1, yln, gx);
       }
+      cp_async_commit();
       if (qload) {
         if (enter) pol.template accum<+1>(curE, cmask, Vi, Vd);
         if (leave) pol.template accum<-1>(curL, cmask, Vi, Vd);
       }
-      curE = nxE; curL = nxL;
     } else {
-      if (qload && (enter || leave)) pol.accum_direct(yin, enter, yl, leave, gx, cmask, Vd);
+      if (qload) {
+        const int ya = yin + 2, yb = yl + 2;  // two rows ahead: towards L2 while this row is worked on
+        if ((t & 7) == 0) {
+          if (ya >= 0 && ya < H && ya < ye + r) pol.prefetch_row(ya, gx);
+          if (yb >= y_first && ya < ye + r) pol.prefetch_row(yb, gx);
+        }
+        if (enter || leave) pol.accum_direct(yin, enter, yl, leave, gx, cmask, Vd);
+      }
     }
     const int yo = yin - r;
-    if (yo < ys) continue;  // warm-up rows (uniform across the CTA)
-
-    // ---- publish the quad prefixes and totals -------------------------------------------------------
-    for (int i = NQ + t; i < GP; i += P::NT) {  // tail of the quad-total rows: keep it finite
-#pragma unroll
-      for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
-#pragma unroll
-      for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
-    }
-    if (qact) {
-#pragma unroll
-      for (int k = 0; k < NI; k++) {
-        uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-        *reinterpret_cast<uint4*>(Pi + (size_t)k * PW + 4 * t) = make_uint4(p0, p1, p2, p3);
-        Gi[k * GP + t] = p3;
-      }
-#pragma unroll
-      for (int k = 0; k < ND; k++) {
-        double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-        double2* d = reinterpret_cast<double2*>(Pd + (size_t)k * PW + 4 * t);
-        d[0] = make_double2(p0, p1);
-        d[1] = make_double2(p2, p3);
-        Gd[k * GP + t] = p3;
-      }
-    }
-    __syncthreads();
-    // ---- prefix over the quad totals (warp-aligned task groups: ints first, then doubles) -----------
-    {
-      constexpr int TI = NI * GF_NSEG, TIP = (TI + 31) & ~31, TD = ND * GF_NSEG;
-      if (t < TIP) {
-        if (NI > 0) gf_scan_task<uint32_t, uint4>(Gi + (size_t)min(t >> 3, NIa - 1) * GP, t & 7, gg.SEGQ, t < TI);
-      } else if (t < TIP + ((TD + 31) & ~31)) {
-        int td = t - TIP;
-        gf_scan_task<double, double2>(Gd + (size_t)min(td >> 3, ND - 1) * GP, td & 7, gg.SEGQ, td < TD);
-      }
-    }
-    __syncthreads();
-    // ---- window sums and the per-pixel work -----------------------------------------------------------
-    if (oact) {
-      const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
-      pol.row_begin(yo, gx);
-      uint32_t si[4][NIa];
-      if (gg.fast) {
+    if (yo >= ys) {  // past the warm-up rows (uniform across the CTA)
+      // ---- publish the quad prefixes and totals -----------------------------------------------------
+      if (qact) {
 #pragma unroll
         for (int k = 0; k < NI; k++) {
-          uint32_t Wq = Gi[k * GP + t + rho - 1] - Gi[k * GP + t - rho - 1];
-          uint4 a = *reinterpret_cast<const uint4*>(Pi + (size_t)k * PW + 4 * (t - rho));
-          uint4 b = *reinterpret_cast<const uint4*>(Pi + (size_t)k * PW + 4 * (t + rho));
-          si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
+          uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+          Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+          Gi[k * GP + t] = p3;
         }
-      } else {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
-#pragma unroll
-          for (int k = 0; k < NI; k++) {
-            uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pi[(size_t)k * PW + zl - 1] : 0u);
-            uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pi[(size_t)k * PW + zh - 1] : 0u);
-            si[c][k] = fh - fl;
-          }
+        for (int k = 0; k < ND; k++) {
+          double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+          Pd01[k * NT + t] = make_double2(p0, p1);
+          Pd23[k * NT + t] = make_double2(p2, p3);
+          Gd[k * GP + t] = p3;
         }
       }
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        double sd[2][ND];
+      __syncthreads();
+      // ---- prefix over the quad totals (warp-aligned task groups: ints first, then doubles) ---------
+      {
+        constexpr int TI = NI * GF_NSEG, TIP = (TI + 31) & ~31, TD = ND * GF_NSEG;
+        if (t < TIP) {
+          if (NI > 0) gf_scan_task<uint32_t, uint4>(Gi + min(t >> 3, NIa - 1) * GP, t & 7, t < TI);
+        } else if (t < TIP + ((TD + 31) & ~31)) {
+          int td = t - TIP;
+          gf_scan_task<double, double2>(Gd + min(td >> 3, ND - 1) * GP, td & 7, td < TD);
+        }
+      }
+      __syncthreads();
+      // ---- window sums and the per-pixel work ---------------------------------------------------------
+      if (oact) {
+        const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
+        pol.row_begin(yo, gx);
+        uint32_t si[4][NIa];
         if (gg.fast) {
 #pragma unroll
-          for (int k = 0; k < ND; k++) {
-            double Wq = Gd[k * GP + t + rho - 1] - Gd[k * GP + t - rho - 1];
-            const double* pa = Pd + (size_t)k * PW + 4 * (t - rho);
-            double2 b = *reinterpret_cast<const double2*>(Pd + (size_t)k * PW + 4 * (t + rho) + 2 * h);
-            if (h == 0) {
-              double a0 = pa[0];
-              sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a0) + b.y;
-            } else {
-              double a1 = pa[1], a2 = pa[2];
-              sd[0][k] = (Wq - a1) + b.x; sd[1][k] = (Wq - a2) + b.y;
-            }
+          for (int k = 0; k < NI; k++) {
+            uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
+            uint4 a = Pi[k * NT + tlo], b = Pi[k * NT + thi];
+            si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
           }
         } else {
+          const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
 #pragma unroll
-          for (int cc = 0; cc < 2; cc++) {
-            int c = 2 * h + cc;
+          for (int c = 0; c < 4; c++) {
             int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
 #pragma unroll
-            for (int k = 0; k < ND; k++) {
-              double fl = Gd[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pd[(size_t)k * PW + zl - 1] : 0.0);
-              double fh = Gd[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pd[(size_t)k * PW + zh - 1] : 0.0);
-              sd[cc][k] = fh - fl;
+            for (int k = 0; k < NI; k++) {
+              uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
+              uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
+              si[c][k] = fh - fl;
             }
           }
         }
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          int x = gx + 2 * h + cc;
-          if (x < W) {
-            int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
-            pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
+        for (int h = 0; h < 2; h++) {
+          double sd[2][ND];
+          if (gg.fast) {
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+              double Wq = Gd[k * GP + thi - 1] - Gd[k * GP + tlo - 1];
+              double2 a01 = Pd01[k * NT + tlo];
+              if (h == 0) {
+                double2 b = Pd01[k * NT + thi];
+                sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a01.x) + b.y;
+              } else {
+                double a2 = Pd23[k * NT + tlo].x;
+                double2 b = Pd23[k * NT + thi];
+                sd[0][k] = (Wq - a01.y) + b.x; sd[1][k] = (Wq - a2) + b.y;
+              }
+            }
+          } else {
+            const double* P01 = reinterpret_cast<const double*>(Pd01);
+            const double* P23 = reinterpret_cast<const double*>(Pd23);
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+              int c = 2 * h + cc;
+              int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+#pragma unroll
+              for (int k = 0; k < ND; k++) {
+                // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd23
+                int el = (zl & 3) - 1, eh = (zh & 3) - 1;
+                double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : P23[(k * NT + (zl >> 2)) * 2]);
+                double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : P23[(k * NT + (zh >> 2)) * 2]);
+                sd[cc][k] = (Gd[k * GP + (zh >> 2) - 1] + ph) - (Gd[k * GP + (zl >> 2) - 1] + pl);
+              }
+            }
           }
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) {
+            int x = gx + 2 * h + cc;
+            if (x < W) {
+              int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
+              pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
+            }
+          }
+          if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
         }
-        if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   pol.finish();
 }
 
 // geometry + launch -------------------------------------------------------------------------------------
-template <class P>
-static size_t gf_smem_bytes(const GfGeom& gg) {
-  size_t PW = (size_t)gg.NQ * 4;
-  return (size_t)P::ND * (PW + gg.GP) * 8 + (size_t)P::NI * (PW + gg.GP) * 4 + sizeof(typename P::Shared);
-}
-
 static GfGeom gf_geometry(int W, int H, int r, int NT) {
   GfGeom g;
   g.W = W; g.H = H; g.Wp = (W + 3) & ~3; g.r = r;
@@ -1010,10 +1078,6 @@ static GfGeom gf_geometry(int W, int H, int r, int NT) {
   int strips = cdiv(W, sw_max);
   g.SW = (cdiv(W, strips) + 3) & ~3;
   g.NQ = 1 + (2 * g.HL + g.SW) / 4;
-  int s4 = cdiv(g.NQ, 4 * GF_NSEG);
-  if ((s4 & 1) == 0) s4++;            // odd number of 16-byte chunks per segment: conflict-free vector loads
-  g.SEGQ = 4 * s4;
-  g.GP = GF_NSEG * g.SEGQ;
   g.seg_h = H;
   g.fast = (r % 4 == 0) ? 1 : 0;
   return g;
@@ -1021,6 +1085,7 @@ static GfGeom gf_geometry(int W, int H, int r, int NT) {
 
 template <class P>
 static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, int W, int H, int r) {
+  static_assert(P::NT <= GF_GP, "quad-total rows hold one entry per thread");
   GfGeom gg = gf_geometry(W, H, r, P::NT);
   int strips = cdiv(W, gg.SW);
   // vertical segments: fill the machine (tail of the last wave) against the 2r warm-up rows per segment
@@ -1037,11 +1102,11 @@ static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, 
   }
   gg.seg_h = cdiv(H, best);
   int segs = cdiv(H, gg.seg_h);
-  size_t smem = gf_smem_bytes<P>(gg);
-  static size_t attr = 0;  // per template instantiation
-  if (smem > attr) {
+  size_t smem = GfSmem<P>::bytes;
+  static bool attr_done = false;  // per template instantiation
+  if (!attr_done) {
     UWIP_CUDA(ctx, cudaFuncSetAttribute(gf_march_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr_done = true;
   }
   dim3 grid(strips, segs, n);
   UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT, smem, gc, gg);
