@@ -77,7 +77,29 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* g) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem, const void* g, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(g), "r"(bytes), "r"(b) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // D0: joint min / max over all channels (bgdehaze/main.py:17)
@@ -464,19 +486,20 @@ __device__ __forceinline__ uint32_t quad_get(const uint4& v, int c) { return c =
 __device__ __forceinline__ float quad_get(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
 
 
-// V-phase of the plane-reading policies (GF1b, GF2b): one plane at a time so that only two quads are
-// in flight per plane; every value goes through fp64 (the a,b planes are f32).
-template <int NP>
-__device__ __forceinline__ void gf_accum_planes(const float* __restrict__ base, size_t n_pp, size_t oE, size_t oL, bool enter, bool leave,
-                                                unsigned cmask, double (&Vd)[4][NP]) {
+// V-phase of the plane-reading policies (GF1b, GF2b): the entering and the leaving row of every plane
+// were brought to shared memory by TMA bulk copies ([2][NP][NT] quads); every value goes through fp64
+// (the a,b planes are f32).
+template <int NP, int NT>
+__device__ __forceinline__ void gf_accum_staged(const float4* __restrict__ stg, bool enter, bool leave, unsigned cmask, double (&Vd)[4][NP]) {
 #pragma unroll
   for (int k = 0; k < NP; k++) {
     float4 e = make_float4(0.f, 0.f, 0.f, 0.f), l = e;
-    if (enter) e = __ldg(reinterpret_cast<const float4*>(base + k * n_pp + oE));
-    if (leave) l = __ldg(reinterpret_cast<const float4*>(base + k * n_pp + oL));
+    if (enter) e = stg[k * NT + threadIdx.x];
+    if (leave) l = stg[(NP + k) * NT + threadIdx.x];
 #pragma unroll
     for (int c = 0; c < 4; c++)
       if (cmask & (1u << c)) Vd[c][k] += (double)quad_get(e, c) - (double)quad_get(l, c);
+    if ((k & 1) == 1) asm volatile("" ::: "memory");  // at most two planes (four quads) in flight: registers
   }
 }
 
@@ -575,7 +598,7 @@ struct PolGF1a {
 
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
-  static constexpr int NI = 0, ND = 8, MINB = 2, MAXREG = 168, NT = 192;
+  static constexpr int NI = 0, ND = 8, MINB = 2, MAXREG = 168, NT = 160;
   static constexpr bool PREFETCH = false;
   struct Shared {
     double nrm[256];
@@ -603,16 +626,8 @@ struct PolGF1b {
     cnt = 0; rmn = 255; rmx = 0; rsum = 0; nanf = 0;
     __syncthreads();
   }
-  static constexpr int STAGE_BYTES = 0;
-  __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
-    gf_accum_planes<8>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
-  }
-  // pull the quads of a later row towards L2 (one request per 128-byte line)
-  __device__ __forceinline__ void prefetch_row(int y, int gx) const {
-    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
-#pragma unroll
-    for (int k = 0; k < 8; k++) prefetch_l2(ab + k * n_pp + o);
-  }
+  static constexpr int NP = 8, STAGE_BYTES = 2 * NP * NT * 16;
+  __device__ __forceinline__ const float* plane(int k) const { return ab + (size_t)k * Wp * H; }
   __device__ __forceinline__ void row_begin(int y, int gx) { krow = __ldg(reinterpret_cast<const uint4*>(kq + (size_t)y * Wp + gx)); }
   __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd) {
     double invN = rcp_fast(u2d((uint32_t)Ncnt));
@@ -744,7 +759,7 @@ struct PolGF2a {
 
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
-  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 192;
+  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 160;
   static constexpr bool PREFETCH = false;
   typedef ExpShared Shared;
   struct Raw {};
@@ -764,15 +779,8 @@ struct PolGF2b {
     exp_shared_init(sh, g.fs[f], (double)gg.W * (double)gg.H);
     omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
   }
-  static constexpr int STAGE_BYTES = 0;
-  __device__ __forceinline__ void accum_direct(int yE, bool enter, int yL, bool leave, int gx, unsigned cmask, double (&Vd)[4][ND]) const {
-    gf_accum_planes<4>(ab, (size_t)Wp * H, (size_t)yE * Wp + gx, (size_t)yL * Wp + gx, enter, leave, cmask, Vd);
-  }
-  __device__ __forceinline__ void prefetch_row(int y, int gx) const {
-    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
-#pragma unroll
-    for (int k = 0; k < 4; k++) prefetch_l2(ab + k * n_pp + o);
-  }
+  static constexpr int NP = 4, STAGE_BYTES = 2 * NP * NT * 16;
+  __device__ __forceinline__ const float* plane(int k) const { return ab + (size_t)k * Wp * H; }
   __device__ __forceinline__ void row_begin(int y, int gx) {
     size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
     krow = __ldg(reinterpret_cast<const uint4*>(kq + o));
@@ -821,34 +829,45 @@ struct PolGF2b {
 // -------------------------------------------------------------------------------------------------
 // One scan task: GF_SEGQ consecutive quad totals of one moment -> inclusive prefix over the whole row.
 // The eight tasks of a moment sit in eight adjacent lanes; their segment totals are exchanged with
-// shuffles.  Every lane of the warp takes part (lanes without a task carry zeros).
+// shuffles.  The segment lives in registers between the load and the store (one pass over shared
+// memory); the in-register prefix is done per group of four to keep the dependent chain short.
 template <class T, class V4>
 __device__ __forceinline__ void gf_scan_task(T* row, int seg, bool live) {
   constexpr int VW = sizeof(V4) / sizeof(T);  // 4 (u32) or 2 (f64)
+  constexpr int NG = GF_SEGQ / 4;             // groups of four values
   T* p = row + seg * GF_SEGQ;
-  T tot = 0;
-  if (live) {
+  T v[GF_SEGQ];
 #pragma unroll
-    for (int i = 0; i < GF_SEGQ; i += VW) {
-      V4 v = *reinterpret_cast<const V4*>(p + i);
-      if constexpr (VW == 4) tot += (v.x + v.y) + (v.z + v.w); else tot += v.x + v.y;
-    }
+  for (int i = 0; i < GF_SEGQ; i += VW) {
+    V4 q;
+    if (live) q = *reinterpret_cast<const V4*>(p + i);
+    if constexpr (VW == 4) { v[i] = live ? q.x : T(0); v[i + 1] = live ? q.y : T(0); v[i + 2] = live ? q.z : T(0); v[i + 3] = live ? q.w : T(0); }
+    else { v[i] = live ? q.x : T(0); v[i + 1] = live ? q.y : T(0); }
   }
-  T incl = tot;
+  T gt[NG];
+#pragma unroll
+  for (int g = 0; g < NG; g++) {  // prefix inside each group of four (independent chains of three)
+    v[4 * g + 1] += v[4 * g]; v[4 * g + 2] += v[4 * g + 1]; v[4 * g + 3] += v[4 * g + 2];
+    gt[g] = v[4 * g + 3];
+  }
+#pragma unroll
+  for (int g = 1; g < NG; g++) gt[g] += gt[g - 1];  // inclusive prefix of the group totals
+  T incl = gt[NG - 1];
 #pragma unroll
   for (int d = 1; d < GF_NSEG; d <<= 1) {
     T o = __shfl_up_sync(0xffffffffu, incl, d, GF_NSEG);
     if (seg >= d) incl += o;
   }
-  T run = __shfl_up_sync(0xffffffffu, incl, 1, GF_NSEG);  // exclusive offset (never derived from this segment's own total)
+  T run = __shfl_up_sync(0xffffffffu, incl, 1, GF_NSEG);  // exclusive offset of this segment
   if (seg == 0) run = 0;
   if (live) {
 #pragma unroll
     for (int i = 0; i < GF_SEGQ; i += VW) {
-      V4 v = *reinterpret_cast<const V4*>(p + i);
-      if constexpr (VW == 4) { v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w; }
-      else { v.x += run; v.y += v.x; run = v.y; }
-      *reinterpret_cast<V4*>(p + i) = v;
+      T off = run + (i >= 4 ? gt[i / 4 - 1] : T(0));
+      V4 q;
+      if constexpr (VW == 4) { q.x = v[i] + off; q.y = v[i + 1] + off; q.z = v[i + 2] + off; q.w = v[i + 3] + off; }
+      else { q.x = v[i] + off; q.y = v[i + 1] + off; }
+      *reinterpret_cast<V4*>(p + i) = q;
     }
   }
 }
@@ -856,7 +875,7 @@ __device__ __forceinline__ void gf_scan_task(T* row, int seg, bool live) {
 // shared-memory layout of one published row; every pitch is a compile-time constant so that each
 // access is base register + immediate:
 //   Pd01 [ND][NT] double2 (prefix 0,1 of the quad) | Pd23 [ND][NT] double2 (prefix 2,3)
-//   Gd [ND][GF_GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GF_GP] u32 | policy tables | cp.async staging
+//   Gd [ND][GF_GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GF_GP] u32 | policy tables | row staging | mbarrier
 template <class P>
 struct GfSmem {
   static constexpr int NT = P::NT, NI = P::NI, ND = P::ND;
@@ -866,11 +885,18 @@ struct GfSmem {
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t off_sh = off_gi + (size_t)NI * GF_GP * 4;
   static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 15) & ~(size_t)15;
-  static constexpr size_t bytes = off_st + P::STAGE_BYTES;
+  static constexpr size_t off_bar = off_st + P::STAGE_BYTES;
+  static constexpr size_t bytes = off_bar + 16;
 };
 
+// Thread roles: threads 0..NT-1 are WORKERS (one quad of the strip each); the last warp is the AUXILIARY
+// warp: it turns the quad totals of the published row into prefixes while the workers already add the
+// next row to their running sums, and (plane readers) its lane 0 is the TMA producer of the row staging.
+//
+// One output row:   workers publish(yo) | bar A | aux scan(yo) || workers acc(row yin+1) | bar B |
+//                   aux TMA(row yin+2) || workers window sums + per-pixel work of yo | bar C
 template <class P>
-__global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
+__global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
   constexpr int NI = P::NI, ND = P::ND, NT = P::NT, GP = GF_GP;
   constexpr int NIa = NI > 0 ? NI : 1;
   typedef GfSmem<P> L;
@@ -881,10 +907,14 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
   uint4* Pi = reinterpret_cast<uint4*>(smem_raw + L::off_pi);
   uint32_t* Gi = reinterpret_cast<uint32_t*>(smem_raw + L::off_gi);
   typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(smem_raw + L::off_sh);
+  unsigned char* stage = smem_raw + L::off_st;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
   P pol;
   pol.init(gc, blockIdx.z, sh, gg);
 
   const int t = threadIdx.x;
+  const bool aux = t >= NT;
+  const int lane = t & 31;
   const int NQ = gg.NQ;
   const int W = gg.W, H = gg.H, r = gg.r;
   const int xs = blockIdx.x * gg.SW;
@@ -898,20 +928,27 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
   const bool qload = cmask != 0;              // then 0 <= gx < Wp: the whole quad is readable
   const int ys = blockIdx.y * gg.seg_h, ye = min(ys + gg.seg_h, H);
   const int y_first = max(ys - r, 0);         // first row that enters the running sums
+  const int y_begin = ys - r, y_end = ye + r; // rows yin of the march
   // output quads of this strip
   const int tq0 = gg.HL / 4 + 1;
   const bool oact = (t >= tq0) && (t < tq0 + gg.SW / 4) && (gx < W);
   const int rho = r >> 2;
   // addresses used by the window sums: the quads at -rho / +rho and the totals around them
   const int tlo = oact ? t - rho : 0, thi = oact ? t + rho : 0;
+  // quads of this strip that lie inside the padded image: [tA, tB) (the guard quad 0 stays zero)
+  const int tA = max(1, (gg.HL + 4 - xs) >> 2), tB = min(NQ, (gg.Wp - xs + gg.HL + 4) >> 2);
 
   // the quad-total rows are scanned over their whole length: keep the unused tail finite
-  for (int i = t; i < GP; i += NT) {
+  for (int i = t; i < GP; i += NT + 32) {
 #pragma unroll
     for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
 #pragma unroll
     for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
   }
+  if constexpr (!P::PREFETCH) {
+    if (t == NT) mbar_init(mbar, 1);
+  }
+  __syncthreads();
 
   uint32_t Vi[4][NIa];
   double Vd[4][ND];
@@ -923,30 +960,43 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
     for (int k = 0; k < ND; k++) Vd[c][k] = 0.0;
   }
 
-  unsigned char* stage = smem_raw + L::off_st;
-  if constexpr (P::PREFETCH) {
-    // rows of the first iteration -> staging buffer 0
-    int yin = ys - r, yl = yin - 2 * r - 1;
-    if (qload && yin >= 0 && yin < H) pol.stage_issue(stage, 0, yin, gx);
-    if (qload && yl >= y_first) pol.stage_issue(stage, 1, yl, gx);
-    cp_async_commit();
-  }
-
-  int buf = 0;
-  for (int yin = ys - r; yin < ye + r; ++yin, buf ^= 1) {
-    const int yl = yin - 2 * r - 1;
-    const bool enter = (yin >= 0 && yin < H), leave = (yl >= y_first);
+  // TMA producer of the plane readers (aux lane 0): the entering and the leaving row of every plane for
+  // march row `yi` land in the staging buffer and complete one mbarrier phase
+  auto tma_rows = [&](int yi) {
+    if constexpr (!P::PREFETCH) {
+      if (yi >= y_end) return;
+      const int yli = yi - 2 * r - 1;
+      const bool en = (yi >= 0 && yi < H), le = (yli >= y_first);
+      const unsigned row_bytes = (unsigned)(tB - tA) * 16u;
+      const unsigned n_rows = (en ? P::NP : 0) + (le ? P::NP : 0);
+      mbar_arrive_expect_tx(mbar, n_rows * row_bytes);
+      float4* stg = reinterpret_cast<float4*>(stage);
+      const int gxa = xs - gg.HL - 4 + 4 * tA;
+#pragma unroll 1
+      for (int k = 0; k < P::NP; k++) {
+        const float* pl = pol.plane(k);
+        if (en) tma_bulk_g2s(stg + k * NT + tA, pl + (size_t)yi * gg.Wp + gxa, row_bytes, mbar);
+        if (le) tma_bulk_g2s(stg + (P::NP + k) * NT + tA, pl + (size_t)yli * gg.Wp + gxa, row_bytes, mbar);
+      }
+    }
+  };
+  // workers: add march row yi to the running sums and drop row yi - 2r - 1
+  auto acc = [&](int yi) {
+    if (yi >= y_end) return;
+    const int yli = yi - 2 * r - 1;
+    const bool enter = (yi >= 0 && yi < H), leave = (yli >= y_first);
+    const int par = (yi - y_begin) & 1;
     if constexpr (P::PREFETCH) {
-      // this iteration's rows were requested one iteration ago; the next iteration's go out now and
-      // stay in flight (no registers held) until the top of the next iteration
+      // this row was requested one march row ago (cp.async, no registers held meanwhile); the next one
+      // goes out now into the other buffer
       cp_async_wait_all();
       typename P::Raw curE, curL;
-      if (qload && enter) pol.stage_read(stage, 2 * buf, curE);
-      if (qload && leave) pol.stage_read(stage, 2 * buf + 1, curL);
-      const int yn = yin + 1, yln = yl + 1;
-      if (qload && yn < ye + r) {
-        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (buf ^ 1), yn, gx);
-        if (yln >= y_first) pol.stage_issue(stage, 2 * (buf ^ 1) + 1, yln, gx);
+      if (qload && enter) pol.stage_read(stage, 2 * par, curE);
+      if (qload && leave) pol.stage_read(stage, 2 * par + 1, curL);
+      const int yn = yi + 1, yln = yli + 1;
+      if (qload && yn < y_end) {
+        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (par ^ 1), yn, gx);
+        if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gx);
       }
       cp_async_commit();
       if (qload) {
@@ -954,117 +1004,140 @@ __global__ void __launch_bounds__(P::NT) __maxnreg__(P::MAXREG) gf_march_kernel(
         if (leave) pol.template accum<-1>(curL, cmask, Vi, Vd);
       }
     } else {
-      if (qload) {
-        const int ya = yin + 2, yb = yl + 2;  // two rows ahead: towards L2 while this row is worked on
-        if ((t & 7) == 0) {
-          if (ya >= 0 && ya < H && ya < ye + r) pol.prefetch_row(ya, gx);
-          if (yb >= y_first && ya < ye + r) pol.prefetch_row(yb, gx);
-        }
-        if (enter || leave) pol.accum_direct(yin, enter, yl, leave, gx, cmask, Vd);
+      mbar_wait(mbar, (unsigned)par);  // phase parity = march row parity
+      if (qload && (enter || leave)) gf_accum_staged<P::NP, NT>(reinterpret_cast<const float4*>(stage), enter, leave, cmask, Vd);
+    }
+  };
+
+  // ---- prologue: first march row ------------------------------------------------------------------
+  if constexpr (P::PREFETCH) {
+    if (!aux) {
+      int yl = y_begin - 2 * r - 1;
+      if (qload && y_begin >= 0 && y_begin < H) pol.stage_issue(stage, 0, y_begin, gx);
+      if (qload && yl >= y_first) pol.stage_issue(stage, 1, yl, gx);
+      cp_async_commit();
+      acc(y_begin);
+    }
+  } else {
+    if (t == NT) tma_rows(y_begin);
+    if (!aux) acc(y_begin);
+    __syncthreads();
+    if (t == NT) tma_rows(y_begin + 1);
+  }
+
+  // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
+  for (int yin = y_begin; yin < y_end; ++yin) {
+    const int yo = yin - r;
+    if (yo < ys) {  // warm-up rows (uniform across the CTA)
+      if (!aux) acc(yin + 1);
+      if constexpr (!P::PREFETCH) {
+        __syncthreads();
+        if (t == NT) tma_rows(yin + 2);
+      }
+      continue;
+    }
+    // ---- publish the quad prefixes and totals -------------------------------------------------------
+    if (qact) {
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+        uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+        Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+        Gi[k * GP + t] = p3;
+      }
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+        double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+        Pd01[k * NT + t] = make_double2(p0, p1);
+        Pd23[k * NT + t] = make_double2(p2, p3);
+        Gd[k * GP + t] = p3;
       }
     }
-    const int yo = yin - r;
-    if (yo >= ys) {  // past the warm-up rows (uniform across the CTA)
-      // ---- publish the quad prefixes and totals -----------------------------------------------------
-      if (qact) {
+    __syncthreads();  // A
+    if (aux) {
+      // prefix over the quad totals, four moments per round (8 lanes each)
+      const int seg = lane & 7, mq = lane >> 3;
+#pragma unroll
+      for (int k0 = 0; k0 < NI; k0 += 4) gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI);
+#pragma unroll
+      for (int k0 = 0; k0 < ND; k0 += 4) gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND);
+    } else {
+      acc(yin + 1);
+    }
+    __syncthreads();  // B
+    if constexpr (!P::PREFETCH) {
+      if (t == NT) tma_rows(yin + 2);  // every worker has consumed the staged rows
+    }
+    // ---- window sums and the per-pixel work -----------------------------------------------------------
+    if (oact) {
+      const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
+      pol.row_begin(yo, gx);
+      uint32_t si[4][NIa];
+      if (gg.fast) {
 #pragma unroll
         for (int k = 0; k < NI; k++) {
-          uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-          Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-          Gi[k * GP + t] = p3;
+          uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
+          uint4 a = Pi[k * NT + tlo], b = Pi[k * NT + thi];
+          si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
         }
+      } else {
+        const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
 #pragma unroll
-        for (int k = 0; k < ND; k++) {
-          double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-          Pd01[k * NT + t] = make_double2(p0, p1);
-          Pd23[k * NT + t] = make_double2(p2, p3);
-          Gd[k * GP + t] = p3;
-        }
-      }
-      __syncthreads();
-      // ---- prefix over the quad totals (warp-aligned task groups: ints first, then doubles) ---------
-      {
-        constexpr int TI = NI * GF_NSEG, TIP = (TI + 31) & ~31, TD = ND * GF_NSEG;
-        if (t < TIP) {
-          if (NI > 0) gf_scan_task<uint32_t, uint4>(Gi + min(t >> 3, NIa - 1) * GP, t & 7, t < TI);
-        } else if (t < TIP + ((TD + 31) & ~31)) {
-          int td = t - TIP;
-          gf_scan_task<double, double2>(Gd + min(td >> 3, ND - 1) * GP, td & 7, td < TD);
-        }
-      }
-      __syncthreads();
-      // ---- window sums and the per-pixel work ---------------------------------------------------------
-      if (oact) {
-        const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
-        pol.row_begin(yo, gx);
-        uint32_t si[4][NIa];
-        if (gg.fast) {
+        for (int c = 0; c < 4; c++) {
+          int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
 #pragma unroll
           for (int k = 0; k < NI; k++) {
-            uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
-            uint4 a = Pi[k * NT + tlo], b = Pi[k * NT + thi];
-            si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
+            uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
+            uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
+            si[c][k] = fh - fl;
           }
-        } else {
-          const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
-#pragma unroll
-            for (int k = 0; k < NI; k++) {
-              uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
-              uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
-              si[c][k] = fh - fl;
-            }
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          double sd[2][ND];
-          if (gg.fast) {
-#pragma unroll
-            for (int k = 0; k < ND; k++) {
-              double Wq = Gd[k * GP + thi - 1] - Gd[k * GP + tlo - 1];
-              double2 a01 = Pd01[k * NT + tlo];
-              if (h == 0) {
-                double2 b = Pd01[k * NT + thi];
-                sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a01.x) + b.y;
-              } else {
-                double a2 = Pd23[k * NT + tlo].x;
-                double2 b = Pd23[k * NT + thi];
-                sd[0][k] = (Wq - a01.y) + b.x; sd[1][k] = (Wq - a2) + b.y;
-              }
-            }
-          } else {
-            const double* P01 = reinterpret_cast<const double*>(Pd01);
-            const double* P23 = reinterpret_cast<const double*>(Pd23);
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-              int c = 2 * h + cc;
-              int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
-#pragma unroll
-              for (int k = 0; k < ND; k++) {
-                // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd23
-                int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-                double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : P23[(k * NT + (zl >> 2)) * 2]);
-                double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : P23[(k * NT + (zh >> 2)) * 2]);
-                sd[cc][k] = (Gd[k * GP + (zh >> 2) - 1] + ph) - (Gd[k * GP + (zl >> 2) - 1] + pl);
-              }
-            }
-          }
-#pragma unroll
-          for (int cc = 0; cc < 2; cc++) {
-            int x = gx + 2 * h + cc;
-            if (x < W) {
-              int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
-              pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
-            }
-          }
-          if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        double sd[2][ND];
+        if (gg.fast) {
+#pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double Wq = Gd[k * GP + thi - 1] - Gd[k * GP + tlo - 1];
+            double2 a01 = Pd01[k * NT + tlo];
+            if (h == 0) {
+              double2 b = Pd01[k * NT + thi];
+              sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a01.x) + b.y;
+            } else {
+              double a2 = Pd23[k * NT + tlo].x;
+              double2 b = Pd23[k * NT + thi];
+              sd[0][k] = (Wq - a01.y) + b.x; sd[1][k] = (Wq - a2) + b.y;
+            }
+          }
+        } else {
+          const double* P01 = reinterpret_cast<const double*>(Pd01);
+          const double* P23 = reinterpret_cast<const double*>(Pd23);
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) {
+            int c = 2 * h + cc;
+            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+              // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd23
+              int el = (zl & 3) - 1, eh = (zh & 3) - 1;
+              double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : P23[(k * NT + (zl >> 2)) * 2]);
+              double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : P23[(k * NT + (zh >> 2)) * 2]);
+              sd[cc][k] = (Gd[k * GP + (zh >> 2) - 1] + ph) - (Gd[k * GP + (zl >> 2) - 1] + pl);
+            }
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          int x = gx + 2 * h + cc;
+          if (x < W) {
+            int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
+            pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
+          }
+        }
+        if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
+      }
     }
+    __syncthreads();  // C
   }
   pol.finish();
 }
@@ -1109,7 +1182,7 @@ static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, 
     attr_done = true;
   }
   dim3 grid(strips, segs, n);
-  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT, smem, gc, gg);
+  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT + 32, smem, gc, gg);
   return UWIP_OK;
 }
 

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Type-check the C++ drop-in shims (and build the tiny host-logic test) against the stand-in OpenCV
+# header; with a real OpenCV pass OPENCV_CFLAGS="$(pkg-config --cflags opencv4)" instead.
+set -e
+cd "$(dirname "$0")"
+CFLAGS=${OPENCV_CFLAGS:--Iopencv_standin}
+g++ -std=c++11 -Wall -Wextra -fsyntax-only $CFLAGS preprocessing_uwip.cpp
+g++ -std=c++11 -Wall -Wextra -fsyntax-only -DUSE_GPU=1 $CFLAGS preprocessing_uwip.cpp
+g++ -std=c++11 -Wall -O1 $CFLAGS shim_test.cpp preprocessing_uwip.cpp -L.. -luwip -Wl,-rpath,"$(cd .. && pwd)" -o shim_test
+echo "shims ok"

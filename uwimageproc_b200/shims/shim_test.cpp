@@ -1,0 +1,45 @@
+// shim_test - exercises the reference-shaped C++ entry points.  Without a GPU it checks the letter
+// maps and that every pixel call fails loudly (no CPU fallback); with `gpu` as argv[1] (B200 box) it
+// checks K0 of SURVEY.md 8c: a 10x10 plane holding 0..99, lo=2, hi=98 -> low=1, high=97, m=2.65625.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "preprocessing.h"
+
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); fails++; } } while (0)
+
+int main(int argc, char** argv) {
+  bool gpu = argc > 1 && !std::strcmp(argv[1], "gpu");
+  // preprocessing.cpp:147-161
+  CHECK(numChannel('R') == 0 && numChannel('G') == 1 && numChannel('B') == 2 && numChannel('V') == 2 && numChannel('r') == -1);
+  CHECK(numSpace('R') == 0 && numSpace('H') == 1 && numSpace('l') == 2 && numSpace('a') == 3 && numSpace('X') == 4 && numSpace('?') == -1);
+  cv::Mat plane(10, 10, CV_8UC1);
+  for (int i = 0; i < 100; i++) plane.at<unsigned char>(i / 10, i % 10) = (unsigned char)i;
+  cv::Mat same = plane;  // header copy sharing the pixels, as at histretch.cpp:236
+  imgChannelStretch(plane, same, 2, 98);
+  if (!gpu) {
+    CHECK(uwipShimLastStatus() != 0);                      // no device: loud failure,
+    CHECK(plane.at<unsigned char>(5, 0) == 50);            // outputs untouched, nothing computed on the CPU
+    std::printf("no-GPU behaviour ok: %s\n", uwipShimLastError());
+  } else {
+    CHECK(uwipShimLastStatus() == 0);
+    for (int i = 0; i < 100; i++) {
+      int x = i - 1 < 0 ? 0 : i - 1;
+      int want = (int)std::nearbyint(x * 2.65625f);
+      if (want > 255) want = 255;
+      CHECK(plane.at<unsigned char>(i / 10, i % 10) == want);
+    }
+    cv::Mat hist;
+    getHistogram(&plane, &hist);
+    CHECK(hist.rows == 256 && hist.cols == 1 && hist.type() == CV_32FC1);
+    float tot = 0;
+    for (int i = 0; i < 256; i++) tot += hist.at<float>(i, 0);
+    CHECK(tot == 100.f);
+    float e = aclaheEntropy(plane);
+    CHECK(e > 0.f && e < 8.f);
+    std::printf("gpu behaviour ok (entropy %.5f)\n", e);
+  }
+  return fails ? 1 : 0;
+}
