@@ -249,6 +249,170 @@ __global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __res
   }
 }
 
+// ---- fast path: both windows 15x15 (the reference's only reachable configuration unless -w is given) ----
+// Tile 64 x 48 outputs, 256 threads.  The window max / min of a run of outputs is formed in registers by
+// doubling: m2[i] = op(p[i], p[i+1]), m4[i] = op(m2[i], m2[i+2]), m8[i] = op(m4[i], m4[i+4]),
+// m15[i] = op(m8[i], m8[i+7])  (4 ops per output instead of 14), on 16-bit pairs (VIMNMX.U16x2).
+constexpr int WF_TX = 64, WF_TY = 48, WF_R = 7, WF_RH = WF_TY + 2 * WF_R;   // 62 region rows
+constexpr int WF_PP = 84;   // region pitch in words: 78 used; 21 x 16 bytes (odd) -> conflict-free 16-byte loads down a column of rows
+constexpr int WF_HP = 68;   // pitch of the horizontal results: 17 x 16 bytes
+
+template <int N, bool MAX>
+__device__ __forceinline__ void win15(const uint32_t (&p)[N + 14], uint32_t (&o)[N]) {
+  uint32_t a[N + 13], b[N + 11], c[N + 7];
+#pragma unroll
+  for (int i = 0; i < N + 13; i++) a[i] = MAX ? __vmaxu2(p[i], p[i + 1]) : __vminu2(p[i], p[i + 1]);
+#pragma unroll
+  for (int i = 0; i < N + 11; i++) b[i] = MAX ? __vmaxu2(a[i], a[i + 2]) : __vminu2(a[i], a[i + 2]);
+#pragma unroll
+  for (int i = 0; i < N + 7; i++) c[i] = MAX ? __vmaxu2(b[i], b[i + 4]) : __vminu2(b[i], b[i + 4]);
+#pragma unroll
+  for (int i = 0; i < N; i++) o[i] = MAX ? __vmaxu2(c[i], c[i + 7]) : __vminu2(c[i], c[i + 7]);
+}
+
+// candidate for the arg-min of D: exact integer difference first (it decides whenever it differs: one
+// unit is 1/range, the fp64 rounding of BGDehaze.py:20-21 is far below that), then the reference's
+// fp64 value, then the flat index
+struct ArgCand { int di; double d; unsigned idx; };
+__device__ __forceinline__ bool cand_less(int ai, double ad, unsigned aidx, int bi, double bd, unsigned bidx) {
+  return (ai < bi) || (ai == bi && ((ad < bd) || (ad == bd && aidx < bidx)));
+}
+
+__global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restrict__ src, int W, int H, int Wp,
+                                                          const FrameState* __restrict__ fs, uint32_t* __restrict__ kq,
+                                                          uint8_t* __restrict__ mgp, ArgPartial* __restrict__ partials) {
+  extern __shared__ __align__(16) uint32_t s_w[];
+  __shared__ double s_nrm[256];
+  __shared__ ArgPartial s_part[8];
+  uint32_t* P0 = s_w;                       // [62][84] (B | G<<16), replicate border
+  uint32_t* P1 = P0 + WF_RH * WF_PP;        // [62][84] R
+  uint32_t* HX0 = P1 + WF_RH * WF_PP;       // [62][68] horizontal max (B,G)
+  uint32_t* HX1 = HX0 + WF_RH * WF_HP;      // horizontal max R
+  uint32_t* HN0 = HX1 + WF_RH * WF_HP;      // horizontal min (B,G)
+  const int f = blockIdx.z, tid = threadIdx.x;
+  const uint8_t* img = src + (size_t)f * W * H * 3;
+  const int x0 = blockIdx.x * WF_TX, y0 = blockIdx.y * WF_TY;
+  const int kmin = fs[f].kmin, range = (int)fs[f].kmax - kmin;
+  s_nrm[tid] = (double)tid / (double)range;  // normI value of k' (main.py:17)
+  // region [y0-7, y0+48+7) x [x0-7, x0+64+7+...) : 62 x 80 pixels (78 used + 2 for the vector loads)
+  for (int i = tid; i < WF_RH * 80; i += 256) {
+    int ry = i / 80, rx = i - ry * 80;
+    int y = min(max(y0 - WF_R + ry, 0), H - 1), x = min(max(x0 - WF_R + rx, 0), W - 1);
+    const uint8_t* p = img + ((size_t)y * W + x) * 3;
+    P0[ry * WF_PP + rx] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 16);
+    P1[ry * WF_PP + rx] = __ldg(p + 2);
+  }
+  __syncthreads();
+  // horizontal: task = (row, run of 8 outputs); consecutive lanes take consecutive rows
+  for (int task = tid; task < WF_RH * 8; task += 256) {
+    int ry = task % WF_RH, j = task / WF_RH;
+    const uint4* r0 = reinterpret_cast<const uint4*>(P0 + ry * WF_PP + 8 * j);
+    const uint4* r1 = reinterpret_cast<const uint4*>(P1 + ry * WF_PP + 8 * j);
+    uint32_t p[22], o[8];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      uint4 v = r0[q];
+      if (4 * q < 22) p[4 * q] = v.x;
+      if (4 * q + 1 < 22) p[4 * q + 1] = v.y;
+      if (4 * q + 2 < 22) p[4 * q + 2] = v.z;
+      if (4 * q + 3 < 22) p[4 * q + 3] = v.w;
+    }
+    win15<8, true>(p, o);
+    uint4* h0 = reinterpret_cast<uint4*>(HX0 + ry * WF_HP + 8 * j);
+    h0[0] = make_uint4(o[0], o[1], o[2], o[3]); h0[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    win15<8, false>(p, o);
+    uint4* hn = reinterpret_cast<uint4*>(HN0 + ry * WF_HP + 8 * j);
+    hn[0] = make_uint4(o[0], o[1], o[2], o[3]); hn[1] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      uint4 v = r1[q];
+      if (4 * q < 22) p[4 * q] = v.x;
+      if (4 * q + 1 < 22) p[4 * q + 1] = v.y;
+      if (4 * q + 2 < 22) p[4 * q + 2] = v.z;
+      if (4 * q + 3 < 22) p[4 * q + 3] = v.w;
+    }
+    win15<8, true>(p, o);
+    uint4* h1 = reinterpret_cast<uint4*>(HX1 + ry * WF_HP + 8 * j);
+    h1[0] = make_uint4(o[0], o[1], o[2], o[3]); h1[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  __syncthreads();
+  // vertical: thread = (column, run of 12 output rows)
+  const int x = tid & 63, run = tid >> 6;
+  const int gx = x0 + x;
+  ArgCand b0 = {0x7fffffff, 0.0, 0xffffffffu}, b1 = b0;
+  if (gx < Wp) {
+    uint32_t p[26], mx0[12], mx1[12], mn0[12];
+    const int ry0 = run * 12;
+#pragma unroll
+    for (int i = 0; i < 26; i++) p[i] = HX0[(ry0 + i) * WF_HP + x];
+    win15<12, true>(p, mx0);
+#pragma unroll
+    for (int i = 0; i < 26; i++) p[i] = HX1[(ry0 + i) * WF_HP + x];
+    win15<12, true>(p, mx1);
+#pragma unroll
+    for (int i = 0; i < 26; i++) p[i] = HN0[(ry0 + i) * WF_HP + x];
+    win15<12, false>(p, mn0);
+    uint32_t* kqf = kq + (size_t)f * Wp * H;
+    uint8_t* mgf = mgp + (size_t)f * Wp * H;
+    const bool xt = (gx < WF_R) || (gx + WF_R >= W);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const int gy = y0 + ry0 + i;
+      if (gy >= H) break;
+      const size_t ppix = (size_t)gy * Wp + gx;
+      if (gx >= W) { kqf[ppix] = 0u; mgf[ppix] = 0; continue; }
+      const bool touches = xt || (gy < WF_R) || (gy + WF_R >= H);
+      const uint32_t c0 = P0[(ry0 + i + WF_R) * WF_PP + x + WF_R], c1 = P1[(ry0 + i + WF_R) * WF_PP + x + WF_R];
+      const uint32_t mb = touches ? 0u : (mn0[i] & 0xffffu) - (uint32_t)kmin;
+      const uint32_t mg = touches ? 0u : (mn0[i] >> 16) - (uint32_t)kmin;
+      kqf[ppix] = ((c0 & 0xffffu) - kmin) | (((c0 >> 16) - kmin) << 8) | ((c1 - kmin) << 16) | (mb << 24);
+      mgf[ppix] = (uint8_t)mg;
+      // D (BGDehaze.py:20-21): max_R - max_B, max_R - max_G on the normalised image
+      const int mr = (int)mx1[i], mB = (int)(mx0[i] & 0xffffu), mG = (int)(mx0[i] >> 16);
+      const unsigned idx = (unsigned)((size_t)gy * W + gx);
+      const int d0i = mr - mB, d1i = mr - mG;
+      if (d0i <= b0.di) {
+        double d = s_nrm[mr - kmin] - s_nrm[mB - kmin];
+        if (cand_less(d0i, d, idx, b0.di, b0.d, b0.idx)) { b0.di = d0i; b0.d = d; b0.idx = idx; }
+      }
+      if (d1i <= b1.di) {
+        double d = s_nrm[mr - kmin] - s_nrm[mG - kmin];
+        if (cand_less(d1i, d, idx, b1.di, b1.d, b1.idx)) { b1.di = d1i; b1.d = d; b1.idx = idx; }
+      }
+    }
+  }
+  // block reduction, lexicographic: first index of the minimum
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    int oi0 = __shfl_xor_sync(0xffffffffu, b0.di, d), oi1 = __shfl_xor_sync(0xffffffffu, b1.di, d);
+    double o0 = __shfl_xor_sync(0xffffffffu, b0.d, d), o1 = __shfl_xor_sync(0xffffffffu, b1.d, d);
+    unsigned j0 = __shfl_xor_sync(0xffffffffu, b0.idx, d), j1 = __shfl_xor_sync(0xffffffffu, b1.idx, d);
+    if (cand_less(oi0, o0, j0, b0.di, b0.d, b0.idx)) { b0.di = oi0; b0.d = o0; b0.idx = j0; }
+    if (cand_less(oi1, o1, j1, b1.di, b1.d, b1.idx)) { b1.di = oi1; b1.d = o1; b1.idx = j1; }
+  }
+  __shared__ int s_di[8][2];
+  if ((tid & 31) == 0) {
+    ArgPartial a; a.d0 = b0.d; a.d1 = b1.d; a.i0 = b0.idx; a.i1 = b1.idx;
+    s_part[tid >> 5] = a; s_di[tid >> 5][0] = b0.di; s_di[tid >> 5][1] = b1.di;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ArgPartial a = s_part[0];
+    int i0 = s_di[0][0], i1 = s_di[0][1];
+    for (int k = 1; k < 8; k++) {
+      ArgPartial b = s_part[k];
+      if (cand_less(s_di[k][0], b.d0, b.i0, i0, a.d0, a.i0)) { i0 = s_di[k][0]; a.d0 = b.d0; a.i0 = b.i0; }
+      if (cand_less(s_di[k][1], b.d1, b.i1, i1, a.d1, a.i1)) { i1 = s_di[k][1]; a.d1 = b.d1; a.i1 = b.i1; }
+    }
+    // empty tile part or NaN D (range 0): leave the "nothing found" marker for bglight_finish_kernel
+    if (!(a.d0 == a.d0)) a.i0 = 0xffffffffu;
+    if (!(a.d1 == a.d1)) a.i1 = 0xffffffffu;
+    if (a.i0 == 0xffffffffu) a.d0 = __longlong_as_double(0x7ff0000000000000ll);
+    if (a.i1 == 0xffffffffu) a.d1 = __longlong_as_double(0x7ff0000000000000ll);
+    partials[(size_t)f * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x] = a;
+  }
+}
+
 // finish the arg-min and form the background light B = mean of the two selected pixels (BGDehaze.py:22-26)
 __global__ void __launch_bounds__(256) bglight_finish_kernel(const uint8_t* __restrict__ src, int W, int H,
                                                              const ArgPartial* __restrict__ partials, int n_part, FrameState* fs,
@@ -1322,32 +1486,39 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   uint8_t* d_mg = (uint8_t*)uwip_slot(ctx, SLOT_MPLANES, (size_t)n * n_pp);
   uint32_t* d_ycc = (uint32_t*)uwip_slot(ctx, SLOT_YCC, (size_t)n * n_pp * 4);
   double* d_stab = (double*)uwip_slot(ctx, SLOT_STAB, (size_t)n * 65536 * 8);
-  dim3 gridw(cdiv(Wp, WK_TX), cdiv(H, WK_TY), n);
-  int n_part = gridw.x * gridw.y;
-  ArgPartial* d_part = (ArgPartial*)uwip_slot(ctx, SLOT_PARTIALS, (size_t)n * n_part * sizeof(ArgPartial));
+  dim3 gridw(cdiv(Wp, WK_TX), cdiv(H, WK_TY), n);    // generic-window kernel
+  dim3 gridf(cdiv(Wp, WF_TX), cdiv(H, WF_TY), n);    // 15x15 kernel
+  int n_part = gridw.x * gridw.y, n_partf = gridf.x * gridf.y;
+  ArgPartial* d_part = (ArgPartial*)uwip_slot(ctx, SLOT_PARTIALS, (size_t)n * std::max(n_part, n_partf) * sizeof(ArgPartial));
   float* d_ab = (float*)uwip_slot(ctx, SLOT_AB, (size_t)n * 8 * n_pp * sizeof(float));
   float* d_J = (float*)uwip_slot(ctx, SLOT_J, (size_t)n * 2 * n_pp * sizeof(float));
   float* d_refS = (float*)uwip_slot(ctx, SLOT_REFS, (size_t)n * n_pp * sizeof(float));
   if (!d_kq || !d_mg || !d_ycc || !d_stab || !d_part || !d_ab || !d_J || !d_refS) return UWIP_ERR_NOMEM;
   {
     const int wmax = p.window, wmin = WK_TWIN;
-    int PL = std::max(wmax / 2, wmin / 2), PR = std::max(wmax - 1 - wmax / 2, wmin - 1 - wmin / 2);
-    int RW = WK_TX + PL + PR, RH = WK_TY + PL + PR;
-    size_t smem = ((size_t)2 * RW * RH + (size_t)3 * RH * WK_TX) * 4;
-    static size_t attr = 0;
-    if (smem > attr) {
-      UWIP_CUDA(ctx, cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
-    }
     if (wmax != WK_TWIN) {
       // Background_light(normI, w) for dehazed_BG's B (BGDehaze.py:51) uses the caller's window ...
+      int PL = std::max(wmax / 2, wmin / 2), PR = std::max(wmax - 1 - wmax / 2, wmin - 1 - wmin / 2);
+      int RW = WK_TX + PL + PR, RH = WK_TY + PL + PR;
+      size_t smem = ((size_t)2 * RW * RH + (size_t)3 * RH * WK_TX) * 4;
+      static size_t attr = 0;
+      if (smem > attr) {
+        UWIP_CUDA(ctx, cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+      }
       UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, Wp, wmax, fs, d_kq, d_mg, d_part);
       UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 1, 0);
     }
     // ... but refined_t() is always called without w (BGDehaze.py:52): the transmission and the
     // background light inside transmission_map use the 15x15 window
-    UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, Wp, WK_TWIN, fs, d_kq, d_mg, d_part);
-    UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, wmax == WK_TWIN ? 1 : 0, 1);
+    size_t smemf = ((size_t)2 * WF_RH * WF_PP + (size_t)3 * WF_RH * WF_HP) * 4;
+    static bool attrf = false;
+    if (!attrf) {
+      UWIP_CUDA(ctx, cudaFuncSetAttribute(window15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
+      attrf = true;
+    }
+    UWIP_LAUNCH(ctx, "dz_window", window15_kernel, gridf, 256, smemf, d_src, W, H, Wp, fs, d_kq, d_mg, d_part);
+    UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_partf, fs, wmax == WK_TWIN ? 1 : 0, 1);
   }
   if (dbg && dbg->stop_after == 1) return UWIP_OK;
   if (dbg && dbg->t_raw) {
