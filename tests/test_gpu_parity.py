@@ -287,3 +287,42 @@ def test_chain_full_size_properties(ctx):
     a = ctx.histretch(fr, "V", 1, 99)
     assert (a == O.histretch_frame(fr, "V", 1, 99)).all()
     assert (ctx.aclahe(a, 2.0, (8, 8)) == O.aclahe_frame(a, 2.0, 8, 8)).all()
+
+
+# ---- frame-batch sharding: ranks are emulated one after the other on one GPU ------------------------
+def test_sharded_stream_equals_single_gpu(ctx):
+    import torch
+
+    from uwimageproc_b200.shard import batches, frame_range
+
+    W, H, total = 480, 270, 11
+    d_in = torch.empty((total, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(d_in, 0x5EED0005, 0, total, W, H)
+    d_out = torch.empty_like(d_in)
+    ctx.chain_dev(d_in, d_out, total, W, H)
+    ctx.synchronize()
+    single = ctx.checksum_dev(d_out, total, W, H)
+    for world in (2, 4):
+        got = np.zeros(total, np.uint64)
+        for rank in range(world):
+            first, count = frame_range(rank, world, total)
+            for f, n in batches(first, count, 2):  # each rank generates ITS frames and runs them in batches of 2
+                b_in = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+                ctx.synth_dev(b_in, 0x5EED0005, f, n, W, H)
+                b_out = torch.empty_like(b_in)
+                ctx.chain_dev(b_in, b_out, n, W, H)
+                ctx.synchronize()
+                got[f:f + n] = ctx.checksum_dev(b_out, n, W, H)
+        assert (got == single).all(), world
+
+
+def test_cpp_shims_on_device():
+    """The reference-shaped C++ entry points (uwimageproc_b200/shims) against K0 of SURVEY 8c."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "uwimageproc_b200", "shims", "shim_test")
+    if not os.path.exists(exe):
+        subprocess.run(["bash", os.path.join(root, "uwimageproc_b200", "shims", "check.sh")], check=True, capture_output=True)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

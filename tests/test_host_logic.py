@@ -1,0 +1,126 @@
+"""CPU tests of the host side: the C ABI surface (library loads, exports every declared symbol, fails
+loudly without a device - no compute calls), and the N>1 frame-batch sharding under gloo, world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "uwip.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(uwip_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from uwimageproc_b200 import _lib
+
+    names = _declared_symbols()
+    assert len(names) >= 40
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libuwip.so does not export %s" % n
+    # the ctypes binding covers the whole header, one to one
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.load().uwip_version() == 100
+
+
+def test_letter_maps_match_reference():
+    """numChannel / numSpace (preprocessing.cpp:147-161) are pure host logic."""
+    from uwimageproc_b200 import _lib
+
+    lib = _lib.load()
+    chan = {"R": 0, "G": 1, "B": 2, "H": 0, "S": 1, "V": 2, "h": 0, "s": 1, "l": 2, "L": 0, "a": 1, "b": 2, "Y": 0, "C": 1, "X": 2, "r": -1, "?": -1}
+    space = {"R": 0, "G": 0, "B": 0, "H": 1, "S": 1, "V": 1, "h": 2, "s": 2, "l": 2, "L": 3, "a": 3, "b": 3, "Y": 4, "C": 4, "X": 4, "r": -1}
+    for c, v in chan.items():
+        assert lib.uwip_num_channel(c.encode()) == v, c
+    for c, v in space.items():
+        assert lib.uwip_num_space(c.encode()) == v, c
+
+
+def test_no_cpu_fallback():
+    """Without an sm_100 device every operation must fail loudly (status -2), never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import uwimageproc_b200 as u
+
+    with pytest.raises(u.UwipError) as e:
+        u.Context(0)
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)
+    # the reference-named Python modules are thin wrappers over the same context: same failure
+    from uwimageproc_b200.modules import bgdehaze
+
+    with pytest.raises(u.UwipError):
+        bgdehaze.Background_light(np.zeros((8, 8, 3), np.uint8) + np.arange(8, dtype=np.uint8)[None, :, None] * 30)
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under uwimageproc_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "uwimageproc_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(d, f)
+
+
+def test_frame_ranges_partition_the_stream():
+    from uwimageproc_b200.shard import batches, frame_range
+
+    for total in [0, 1, 7, 256, 10000]:
+        for world in [1, 2, 4, 8]:
+            got = []
+            for r in range(world):
+                f, c = frame_range(r, world, total)
+                got += list(range(f, f + c))
+            assert got == list(range(total))
+            sizes = [frame_range(r, world, total)[1] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    assert batches(10, 7, 3) == [(10, 3), (13, 3), (16, 1)]
+    with pytest.raises(ValueError):
+        frame_range(2, 2, 10)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+from uwimageproc_b200.shard import frame_range, gather_checksums
+from uwimageproc_b200.api import host_checksum
+from oracle import uwip_oracle as O   # test infrastructure: frames for the checksums
+
+rank, world, total = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(sys.argv[2])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+first, count = frame_range(rank, world, total)
+frames = np.stack([O.synth_frame(0x5EED0005, first + i, 64, 36) for i in range(count)]) if count else np.zeros((0, 36, 64, 3), np.uint8)
+sums = host_checksum(frames) if count else np.zeros(0, np.uint64)
+allsums = gather_checksums(sums, rank, world, total, dist)
+ref = host_checksum(np.stack([O.synth_frame(0x5EED0005, i, 64, 36) for i in range(total)]))
+assert (allsums == ref).all(), (rank, allsums, ref)
+dist.barrier()
+dist.destroy_process_group()
+print("rank %d ok %d frames" % (rank, count))
+"""
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """world_size 2 over gloo on the CPU: disjoint contiguous ranges, per-frame checksums gathered in stream
+    order equal the single-process checksums (the frames themselves never cross ranks)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 500), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, "7"], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, outs[r]
+    assert "rank 0 ok 4 frames" in outs[0] and "rank 1 ok 3 frames" in outs[1]

@@ -294,13 +294,20 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
   const int x0 = blockIdx.x * WF_TX, y0 = blockIdx.y * WF_TY;
   const int kmin = fs[f].kmin, range = (int)fs[f].kmax - kmin;
   s_nrm[tid] = (double)tid / (double)range;  // normI value of k' (main.py:17)
-  // region [y0-7, y0+48+7) x [x0-7, x0+64+7+...) : 62 x 80 pixels (78 used + 2 for the vector loads)
-  for (int i = tid; i < WF_RH * 80; i += 256) {
-    int ry = i / 80, rx = i - ry * 80;
-    int y = min(max(y0 - WF_R + ry, 0), H - 1), x = min(max(x0 - WF_R + rx, 0), W - 1);
-    const uint8_t* p = img + ((size_t)y * W + x) * 3;
-    P0[ry * WF_PP + rx] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 16);
-    P1[ry * WF_PP + rx] = __ldg(p + 2);
+  // region [y0-7, y0+48+7) x [x0-7, x0+73) : 62 x 80 pixels (78 used + 2 for the vector loads).
+  // thread = (column, row mod 3); the loads of several rows are issued before the first use
+  if (tid < 240) {
+    const int rx = tid % 80, rr = tid / 80;
+    const int xc = min(max(x0 - WF_R + rx, 0), W - 1);
+    const uint8_t* col = img + (size_t)xc * 3;
+#pragma unroll 7
+    for (int ry = rr; ry < WF_RH; ry += 3) {
+      const int y = min(max(y0 - WF_R + ry, 0), H - 1);
+      const uint8_t* p = col + (size_t)y * W * 3;
+      uint32_t b = __ldg(p), g = __ldg(p + 1), r = __ldg(p + 2);
+      P0[ry * WF_PP + rx] = b | (g << 16);
+      P1[ry * WF_PP + rx] = r;
+    }
   }
   __syncthreads();
   // horizontal: task = (row, run of 8 outputs); consecutive lanes take consecutive rows
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
   const int x = tid & 63, run = tid >> 6;
   const int gx = x0 + x;
   ArgCand b0 = {0x7fffffff, 0.0, 0xffffffffu}, b1 = b0;
+  int bp0 = -1, bp1 = -1;  // (max_R, max_X) pair of the current best: the same pair further down can never win (same D, larger index)
   if (gx < Wp) {
     uint32_t p[26], mx0[12], mx1[12], mn0[12];
     const int ry0 = run * 12;
@@ -371,13 +379,14 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
       const int mr = (int)mx1[i], mB = (int)(mx0[i] & 0xffffu), mG = (int)(mx0[i] >> 16);
       const unsigned idx = (unsigned)((size_t)gy * W + gx);
       const int d0i = mr - mB, d1i = mr - mG;
-      if (d0i <= b0.di) {
+      const int pr0 = (mr << 8) | mB, pr1 = (mr << 8) | mG;
+      if (d0i <= b0.di && pr0 != bp0) {
         double d = s_nrm[mr - kmin] - s_nrm[mB - kmin];
-        if (cand_less(d0i, d, idx, b0.di, b0.d, b0.idx)) { b0.di = d0i; b0.d = d; b0.idx = idx; }
+        if (d0i < b0.di || d < b0.d) { b0.di = d0i; b0.d = d; b0.idx = idx; bp0 = pr0; }  // rows go down: idx only grows
       }
-      if (d1i <= b1.di) {
+      if (d1i <= b1.di && pr1 != bp1) {
         double d = s_nrm[mr - kmin] - s_nrm[mG - kmin];
-        if (cand_less(d1i, d, idx, b1.di, b1.d, b1.idx)) { b1.di = d1i; b1.d = d; b1.idx = idx; }
+        if (d1i < b1.di || d < b1.d) { b1.di = d1i; b1.d = d; b1.idx = idx; bp1 = pr1; }
       }
     }
   }
@@ -677,7 +686,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224;
-  static constexpr bool PREFETCH = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -763,7 +772,7 @@ struct PolGF1a {
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 2, MAXREG = 168, NT = 160;
-  static constexpr bool PREFETCH = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false;
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -848,7 +857,7 @@ struct PolGF1b {
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224;
-  static constexpr bool PREFETCH = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -924,7 +933,7 @@ struct PolGF2a {
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 160;
-  static constexpr bool PREFETCH = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false;
   typedef ExpShared Shared;
   struct Raw {};
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1235,29 +1244,43 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
     if (oact) {
       const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
       pol.row_begin(yo, gx);
-      uint32_t si[4][NIa];
-      if (gg.fast) {
-#pragma unroll
-        for (int k = 0; k < NI; k++) {
-          uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
-          uint4 a = Pi[k * NT + tlo], b = Pi[k * NT + thi];
-          si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
-        }
-      } else {
-        const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+      // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
+      // that trade loads for registers (INT_HALF) - two columns per half
+      uint32_t si[P::INT_HALF ? 2 : 4][NIa];
+      auto int_sums = [&](int h) {
+        if (gg.fast) {
 #pragma unroll
           for (int k = 0; k < NI; k++) {
-            uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
-            uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
-            si[c][k] = fh - fl;
+            uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
+            uint4 a = Pi[k * NT + tlo];
+            if constexpr (!P::INT_HALF) {
+              uint4 b = Pi[k * NT + thi];
+              si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
+            } else {
+              uint2 b = reinterpret_cast<const uint2*>(Pi + k * NT + thi)[h];
+              if (h == 0) { si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; }
+              else { si[0][k] = Wq - a.y + b.x; si[1][k] = Wq - a.z + b.y; }
+            }
+          }
+        } else {
+          const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
+#pragma unroll
+          for (int cc = 0; cc < (P::INT_HALF ? 2 : 4); cc++) {
+            int c = P::INT_HALF ? 2 * h + cc : cc;
+            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
+#pragma unroll
+            for (int k = 0; k < NI; k++) {
+              uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
+              uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
+              si[cc][k] = fh - fl;
+            }
           }
         }
-      }
+      };
+      if constexpr (!P::INT_HALF) int_sums(0);
 #pragma unroll
       for (int h = 0; h < 2; h++) {
+        if constexpr (P::INT_HALF) int_sums(h);
         double sd[2][ND];
         if (gg.fast) {
 #pragma unroll
@@ -1295,7 +1318,7 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
           int x = gx + 2 * h + cc;
           if (x < W) {
             int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
-            pol.column(cc, yo, x, ny * nx, si[2 * h + cc], sd[cc]);
+            pol.column(cc, yo, x, ny * nx, si[P::INT_HALF ? cc : 2 * h + cc], sd[cc]);
           }
         }
         if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
