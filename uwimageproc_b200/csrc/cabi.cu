@@ -474,10 +474,10 @@ static int32_t* flags_get(uwip_ctx* ctx, int n) {
   return f;
 }
 
-// sub-batch size: the dehaze workspace is 56 B/px/frame (+ a 512 KB table); keep it below ~48 GB of the
+// sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 512 KB table); keep it below ~48 GB of the
 // 180 GB and split the batch into equal parts so that no part ends up much smaller than the others
 static int sub_batch(int n, int w, int h) {
-  size_t per_frame = (size_t)w * h * 56 + (512u << 10);
+  size_t per_frame = (size_t)w * h * 60 + (512u << 10);
   size_t cap = std::max<size_t>(1, (size_t)48e9 / per_frame);
   size_t parts = ((size_t)n + cap - 1) / cap;
   return (int)(((size_t)n + parts - 1) / parts);

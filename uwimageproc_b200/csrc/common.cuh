@@ -63,6 +63,7 @@ enum Slot {
   SLOT_KQ,            // dehaze: packed k'_b k'_g k'_r m'_b (u32)
   SLOT_YCC,           // dehaze: packed Yi Cri Cbi Yj (u32)
   SLOT_STAB,          // dehaze: exposure-ratio table (f64 x 65536 per frame)
+  SLOT_SPLANE,        // dehaze: exposure ratio per pixel (f32)
 };
 
 const char* uwip_set_err(uwip_ctx* ctx, const char* fmt, ...);

@@ -526,6 +526,7 @@ struct GfCommon {
   const uint8_t* mg;      // [n][H][Wp] m'_g
   uint32_t* ycc;          // [n][H][Wp] packed Yi Cri Cbi Yj
   const double* stab;     // [n][256][256] exposure ratio S(yi', yj')
+  float* splane;          // [n][H][Wp] S per pixel (f32)
   float* ab;              // [n][8][H][Wp]
   float* J;               // [n][2][H][Wp]
   float* refS;            // [n][H][Wp]
@@ -859,9 +860,9 @@ struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224;
   static constexpr bool PREFETCH = true, INT_HALF = false;
   struct Shared { FrameConst fc; };
-  struct Raw { uint4 y; };
+  struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
-  const uint32_t* ycc; const double* stab; float* ab;
+  const uint32_t* ycc; const float* sp; float* ab;
   uint32_t ysub;   // (yi_min, yi_min, yi_min, yj_min): no byte can borrow
   double epsN_k; unsigned nanf;
   float o[2][4];
@@ -869,7 +870,7 @@ struct PolGF2a {
     g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
     size_t n_pp = (size_t)Wp * H;
     ycc = g.ycc + (size_t)f * n_pp;
-    stab = g.stab + (size_t)f * 65536;
+    sp = g.splane + (size_t)f * n_pp;
     ab = g.ab + (size_t)f * 8 * n_pp;
     if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
     __syncthreads();
@@ -879,12 +880,16 @@ struct PolGF2a {
     ysub = a | (a << 8) | (a << 16) | (b << 24);
     nanf = 0;
   }
-  static constexpr int STAGE_BYTES = 4 * NT * 16;
+  // staging slot s of this thread: the packed guide quad and the S quad
+  static constexpr int STAGE_BYTES = 4 * NT * 32;
   __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx) const {
-    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 16, ycc + (size_t)y * Wp + gx);
+    size_t o = (size_t)y * Wp + gx;
+    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 32, ycc + o);
+    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 32 + 16, sp + o);
   }
   __device__ __forceinline__ void stage_read(const unsigned char* st, int s, Raw& r) const {
-    r.y = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 16);
+    r.y = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 32);
+    r.s = *reinterpret_cast<const float4*>(st + ((size_t)s * NT + threadIdx.x) * 32 + 16);
   }
   template <int SIGN>
   __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI], double (&Vd)[4][ND]) {
@@ -892,8 +897,8 @@ struct PolGF2a {
     for (int c = 0; c < 4; c++) {
       if (cmask & (1u << c)) {
         uint32_t w = quad_get(r.y, c) - ysub;
-        uint32_t g0 = w & 255u, g1 = (w >> 8) & 255u, g2 = (w >> 16) & 255u, yj = w >> 24;
-        double S = __ldg(stab + ((g0 << 8) | yj));
+        uint32_t g0 = w & 255u, g1 = (w >> 8) & 255u, g2 = (w >> 16) & 255u;
+        double S = (double)quad_get(r.s, c);
         if (SIGN > 0) {
           if (!(S == S)) nanf = 1u;
           Vi[c][0] += g0; Vi[c][1] += g1; Vi[c][2] += g2;
@@ -1433,6 +1438,33 @@ __global__ void __launch_bounds__(256) stab_kernel(const FrameState* __restrict_
   stab[(size_t)f * 65536 + gy * 256 + j] = (yj * yi + yi2) / (yj * yj + yi2);
 }
 
+// S per pixel as an f32 plane: GF2a then reads it through the same staged row copies as the guide instead
+// of gathering from the table inside the march (f32 keeps 2^-24 relative: far inside the 1e-5 budget).
+__global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) {
+  int f = blockIdx.y;
+  size_t n_pp = (size_t)Wp * H;
+  const FrameState& s = g.fs[f];
+  const uint32_t a = s.yi_min, b = s.yj_min;
+  const uint32_t ysub = a | (a << 8) | (a << 16) | (b << 24);
+  const uint32_t* ycc = g.ycc + (size_t)f * n_pp;
+  const double* stab = g.stab + (size_t)f * 65536;
+  float* sp = g.splane + (size_t)f * n_pp;
+  const size_t n_q = n_pp / 4;
+  for (size_t qi = (size_t)blockIdx.x * 256 + threadIdx.x; qi < n_q; qi += (size_t)gridDim.x * 256) {
+    uint4 yw = __ldg(reinterpret_cast<const uint4*>(ycc) + qi);
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t w = quad_get(yw, c);
+      // pad columns hold zeros: keep them away from the table (their S is never used)
+      bool pad = (w & 255u) < a || (w >> 24) < b;
+      w -= ysub;
+      o[c] = pad ? 0.f : (float)__ldg(stab + (((w & 255u) << 8) | (w >> 24)));
+    }
+    reinterpret_cast<float4*>(sp)[qi] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
 __global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
   __shared__ ExpShared sh;
@@ -1509,6 +1541,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   uint8_t* d_mg = (uint8_t*)uwip_slot(ctx, SLOT_MPLANES, (size_t)n * n_pp);
   uint32_t* d_ycc = (uint32_t*)uwip_slot(ctx, SLOT_YCC, (size_t)n * n_pp * 4);
   double* d_stab = (double*)uwip_slot(ctx, SLOT_STAB, (size_t)n * 65536 * 8);
+  float* d_sp = (float*)uwip_slot(ctx, SLOT_SPLANE, (size_t)n * n_pp * sizeof(float));
   dim3 gridw(cdiv(Wp, WK_TX), cdiv(H, WK_TY), n);    // generic-window kernel
   dim3 gridf(cdiv(Wp, WF_TX), cdiv(H, WF_TY), n);    // 15x15 kernel
   int n_part = gridw.x * gridw.y, n_partf = gridf.x * gridf.y;
@@ -1516,7 +1549,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   float* d_ab = (float*)uwip_slot(ctx, SLOT_AB, (size_t)n * 8 * n_pp * sizeof(float));
   float* d_J = (float*)uwip_slot(ctx, SLOT_J, (size_t)n * 2 * n_pp * sizeof(float));
   float* d_refS = (float*)uwip_slot(ctx, SLOT_REFS, (size_t)n * n_pp * sizeof(float));
-  if (!d_kq || !d_mg || !d_ycc || !d_stab || !d_part || !d_ab || !d_J || !d_refS) return UWIP_ERR_NOMEM;
+  if (!d_kq || !d_mg || !d_ycc || !d_stab || !d_sp || !d_part || !d_ab || !d_J || !d_refS) return UWIP_ERR_NOMEM;
   {
     const int wmax = p.window, wmin = WK_TWIN;
     if (wmax != WK_TWIN) {
@@ -1551,7 +1584,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   if (dbg && dbg->stop_after == 2) return UWIP_OK;
 
   GfCommon gc;
-  gc.kq = d_kq; gc.mg = d_mg; gc.ycc = d_ycc; gc.stab = d_stab; gc.ab = d_ab; gc.J = d_J; gc.refS = d_refS; gc.fs = fs;
+  gc.kq = d_kq; gc.mg = d_mg; gc.ycc = d_ycc; gc.stab = d_stab; gc.splane = d_sp; gc.ab = d_ab; gc.J = d_J; gc.refS = d_refS; gc.fs = fs;
   gc.eps = p.eps; gc.tmin = p.tmin; gc.dbg_tref = dbg ? dbg->t_ref : nullptr;
   UWIP_CHECK(gf_launch<PolGF1a>(ctx, "dz_gf1a", gc, n, W, H, p.radius));
   UWIP_CHECK(gf_launch<PolGF1b>(ctx, "dz_gf1b", gc, n, W, H, p.radius));
@@ -1562,6 +1595,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   if (dbg && dbg->stop_after == 4) return UWIP_OK;
   dim3 grid_s(256, n);
   UWIP_LAUNCH(ctx, "dz_stab", stab_kernel, grid_s, 256, 0, fs, d_stab);
+  UWIP_LAUNCH(ctx, "dz_splane", splane_kernel, grid_e, 256, 0, gc, H, Wp);
   UWIP_CHECK(gf_launch<PolGF2a>(ctx, "dz_gf2a", gc, n, W, H, p.radius));
   UWIP_CHECK(gf_launch<PolGF2b>(ctx, "dz_gf2b", gc, n, W, H, p.radius));
   UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, Wp, d_dst, dbg ? dbg->out : (double*)nullptr, d_flags);
