@@ -660,20 +660,60 @@ __device__ __forceinline__ uint32_t quad_get(const uint4& v, int c) { return c =
 __device__ __forceinline__ float quad_get(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
 
 
-// V-phase of the plane-reading policies (GF1b, GF2b): the entering and the leaving row of every plane
-// were brought to shared memory by TMA bulk copies ([2][NP][NT] quads); every value goes through fp64
-// (the a,b planes are f32).
+// Coefficient rows (the a,b of a guided filter) are stored quad-interleaved: per image row, per quad of
+// four pixels, NP/4 sixteen-byte chunks per pixel (chunk = a0,a1,a2,b of one filter) - 128 bytes per quad
+// for GF1 (two filters), 64 for GF2.  The chunk order inside a quad is XOR-swizzled with the quad index
+// so that the V-phase of the reader (one thread per quad, a 16-byte shared load per chunk) is free of
+// bank conflicts although consecutive lanes are a whole quad apart.  Writer and reader are both ours.
+template <int NP>
+__device__ __forceinline__ int coef_chunk(int gq, int c, int j) {  // physical chunk of (pixel c, filter j) in quad gq
+  if (NP == 8) return (2 * c + j) ^ (gq & 7);
+  return c ^ ((gq >> 1) & 3);
+}
+
+// V-phase of the coefficient readers (GF1b, GF2b): the entering and the leaving row were brought to shared
+// memory by one TMA bulk copy each ([2][NT quads][NP chunks]); every value goes through fp64.
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <int NP, int NT, bool ENTER, bool LEAVE, bool FULL>
+__device__ __forceinline__ void gf_accum_staged_case(const float4* __restrict__ stg, int gq, unsigned cmask, double (&Vd)[4][NP]) {
+  // quad blocks are NP*16 bytes and block-aligned, so (logical chunk ^ swizzle) * 16 is the block address
+  // with the swizzle folded in, XOR a compile-time constant: one LOP3 per load
+  const unsigned swz = (unsigned)coef_chunk<NP>(gq, 0, 0) << 4;
+  const unsigned be = (unsigned)__cvta_generic_to_shared(stg + (size_t)threadIdx.x * NP) + swz;
+  const unsigned bl = (unsigned)__cvta_generic_to_shared(stg + (size_t)(NT + threadIdx.x) * NP) + swz;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+#pragma unroll
+    for (int j = 0; j < NP / 4; j++) {
+      const unsigned q16 = (unsigned)(NP == 8 ? 2 * c + j : c) << 4;
+      float4 e, l;
+      if (ENTER) e = lds128(be ^ q16);
+      if (LEAVE) l = lds128(bl ^ q16);
+      if (FULL || (cmask & (1u << c))) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (ENTER && LEAVE) Vd[c][4 * j + m] += (double)quad_get(e, m) - (double)quad_get(l, m);
+          else if (ENTER) Vd[c][4 * j + m] += (double)quad_get(e, m);
+          else Vd[c][4 * j + m] -= (double)quad_get(l, m);
+        }
+      }
+    }
+  }
+}
+// uniform dispatch: steady state (both rows, all four columns inside the image) is the straight-line case
 template <int NP, int NT>
-__device__ __forceinline__ void gf_accum_staged(const float4* __restrict__ stg, bool enter, bool leave, unsigned cmask, double (&Vd)[4][NP]) {
-#pragma unroll
-  for (int k = 0; k < NP; k++) {
-    float4 e = make_float4(0.f, 0.f, 0.f, 0.f), l = e;
-    if (enter) e = stg[k * NT + threadIdx.x];
-    if (leave) l = stg[(NP + k) * NT + threadIdx.x];
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-      if (cmask & (1u << c)) Vd[c][k] += (double)quad_get(e, c) - (double)quad_get(l, c);
-    if ((k & 1) == 1) asm volatile("" ::: "memory");  // at most two planes (four quads) in flight: registers
+__device__ __forceinline__ void gf_accum_staged(const float4* __restrict__ stg, int gq, bool enter, bool leave, unsigned cmask, double (&Vd)[4][NP]) {
+  if (enter && leave) {
+    if (cmask == 0xfu) gf_accum_staged_case<NP, NT, true, true, true>(stg, gq, cmask, Vd);
+    else gf_accum_staged_case<NP, NT, true, true, false>(stg, gq, cmask, Vd);
+  } else if (enter) {
+    gf_accum_staged_case<NP, NT, true, false, false>(stg, gq, cmask, Vd);
+  } else if (leave) {
+    gf_accum_staged_case<NP, NT, false, true, false>(stg, gq, cmask, Vd);
   }
 }
 
@@ -686,7 +726,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
-  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224;
+  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
@@ -724,7 +764,7 @@ struct PolGF1a {
     r.k = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 16);
     r.m = *reinterpret_cast<const uint32_t*>(st + (size_t)4 * NT * 16 + ((size_t)s * NT + threadIdx.x) * 4);
   }
-  template <int SIGN>
+  template <int SIGN, bool FULL>
   __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI > 0 ? NI : 1], double (&Vd)[4][ND]) const {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -739,7 +779,7 @@ struct PolGF1a {
         Vi[c][3] -= kb * kb; Vi[c][4] -= kb * kg; Vi[c][5] -= kb * kr;
         Vi[c][6] -= kg * kg; Vi[c][7] -= kg * kr; Vi[c][8] -= kr * kr;
       }
-      if (cmask & (1u << c)) {
+      if (FULL || (cmask & (1u << c))) {
         double pb = sh->pT[0][mb], pg = sh->pT[1][mgv];
         if (SIGN < 0) { pb = -pb; pg = -pg; }
         double db = u2d(kb), dg = u2d(kg), dr = u2d(kr);
@@ -751,20 +791,19 @@ struct PolGF1a {
     }
   }
   __device__ __forceinline__ void row_begin(int, int) {}
-  // results go out column by column (4-byte stores): holding a pair back costs 16 registers that the
-  // 17 running sums x 4 columns do not leave
+  // results go out pixel by pixel: two 16-byte chunks (one per filter) into the swizzled quad block
   __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
     double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
     double M[6], Sd[3], A[6], rdet;
     gf_build_M(si, N, epsN_k * N * N, M, Sd);
     gf_adjugate(M, A, rdet);
     double a[3], b;
-    size_t n_pp = (size_t)Wp * H;
-    float* o = ab + (size_t)y * Wp + x;
+    const int gq = x >> 2, c = x & 3;
+    float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 8;
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
-    o[0] = (float)a[0]; o[n_pp] = (float)a[1]; o[2 * n_pp] = (float)a[2]; o[3 * n_pp] = (float)b;
+    blk[coef_chunk<8>(gq, c, 0)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
     gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
-    o[4 * n_pp] = (float)a[0]; o[5 * n_pp] = (float)a[1]; o[6 * n_pp] = (float)a[2]; o[7 * n_pp] = (float)b;
+    blk[coef_chunk<8>(gq, c, 1)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
   }
   __device__ __forceinline__ void store_pair(int, int) {}
   __device__ void finish() {}
@@ -772,7 +811,7 @@ struct PolGF1a {
 
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
-  static constexpr int NI = 0, ND = 8, MINB = 2, MAXREG = 168, NT = 160;
+  static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false;
   struct Shared {
     double nrm[256];
@@ -786,8 +825,10 @@ struct PolGF1b {
   unsigned cnt, rmn, rmx, rsum, nanf;
   uint4 krow;
   float o[2][2];
+  double* dbg;   // stage-wise API only: refined t of frame 0
   __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
     g = gc; sh = s; W = gg.W; Wp = gg.Wp; H = gg.H; f = frame;
+    dbg = (frame == 0) ? gc.dbg_tref : nullptr;
     size_t n_pp = (size_t)Wp * H;
     kq = g.kq + (size_t)f * n_pp;
     ab = g.ab + (size_t)f * 8 * n_pp;
@@ -801,7 +842,7 @@ struct PolGF1b {
     __syncthreads();
   }
   static constexpr int NP = 8, STAGE_BYTES = 2 * NP * NT * 16;
-  __device__ __forceinline__ const float* plane(int k) const { return ab + (size_t)k * Wp * H; }
+  __device__ __forceinline__ const float* coef_rows() const { return ab; }
   __device__ __forceinline__ void row_begin(int y, int gx) { krow = __ldg(reinterpret_cast<const uint4*>(kq + (size_t)y * Wp + gx)); }
   __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd) {
     double invN = rcp_fast(u2d((uint32_t)Ncnt));
@@ -812,7 +853,7 @@ struct PolGF1b {
     for (int c = 0; c < 2; c++) {
       const double* s = sd + 4 * c;
       double q = (s[0] * kd[0] + s[1] * kd[1] + s[2] * kd[2] + s[3]) * invN;   // guidedfilter.py:100-101
-      if (g.dbg_tref && f == 0) g.dbg_tref[(size_t)c * W * H + (size_t)y * W + x] = q;
+      if (dbg) dbg[(size_t)c * W * H + (size_t)y * W + x] = q;
       double Bc = sh->fc.B[c];
       double Jv = (sh->nrm[k[c]] - Bc) * rcp_fast(q) + Bc;                    // BGDehaze.py:53,55
       float Jf = (float)Jv;
@@ -857,7 +898,7 @@ struct PolGF1b {
 
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
-  static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224;
+  static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
@@ -865,7 +906,6 @@ struct PolGF2a {
   const uint32_t* ycc; const float* sp; float* ab;
   uint32_t ysub;   // (yi_min, yi_min, yi_min, yj_min): no byte can borrow
   double epsN_k; unsigned nanf;
-  float o[2][4];
   __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
     g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
     size_t n_pp = (size_t)Wp * H;
@@ -891,11 +931,11 @@ struct PolGF2a {
     r.y = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 32);
     r.s = *reinterpret_cast<const float4*>(st + ((size_t)s * NT + threadIdx.x) * 32 + 16);
   }
-  template <int SIGN>
+  template <int SIGN, bool FULL>
   __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI], double (&Vd)[4][ND]) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      if (cmask & (1u << c)) {
+      if (FULL || (cmask & (1u << c))) {
         uint32_t w = quad_get(r.y, c) - ysub;
         uint32_t g0 = w & 255u, g1 = (w >> 8) & 255u, g2 = (w >> 16) & 255u;
         double S = (double)quad_get(r.s, c);
@@ -916,19 +956,17 @@ struct PolGF2a {
     }
   }
   __device__ __forceinline__ void row_begin(int, int) {}
-  __device__ __forceinline__ void column(int cc, int, int, int Ncnt, const uint32_t* si, const double* sd) {
+  __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
     double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
     double M[6], Sd[3], A[6], rdet, a[3], b;
     gf_build_M(si, N, epsN_k * N * N, M, Sd);
     gf_adjugate(M, A, rdet);
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 1, a, b);
-    o[cc][0] = (float)a[0]; o[cc][1] = (float)a[1]; o[cc][2] = (float)a[2]; o[cc][3] = (float)b;
+    const int gq = x >> 2;
+    float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 4;
+    blk[coef_chunk<4>(gq, x & 3, 0)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
   }
-  __device__ __forceinline__ void store_pair(int y, int x) {
-    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
-#pragma unroll
-    for (int k = 0; k < 4; k++) *reinterpret_cast<float2*>(ab + k * n_pp + pp) = make_float2(o[0][k], o[1][k]);
-  }
+  __device__ __forceinline__ void store_pair(int, int) {}
   __device__ void finish() {
     unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
     if ((threadIdx.x & 31) == 0 && nf) atomicOr(&g.fs[f].nan_flag, 1u);
@@ -937,7 +975,7 @@ struct PolGF2a {
 
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
-  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 160;
+  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 160, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false;
   typedef ExpShared Shared;
   struct Raw {};
@@ -958,7 +996,7 @@ struct PolGF2b {
     omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
   }
   static constexpr int NP = 4, STAGE_BYTES = 2 * NP * NT * 16;
-  __device__ __forceinline__ const float* plane(int k) const { return ab + (size_t)k * Wp * H; }
+  __device__ __forceinline__ const float* coef_rows() const { return ab; }
   __device__ __forceinline__ void row_begin(int y, int gx) {
     size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
     krow = __ldg(reinterpret_cast<const uint4*>(kq + o));
@@ -1062,7 +1100,7 @@ struct GfSmem {
   static constexpr size_t off_pi = off_gd + (size_t)ND * GF_GP * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t off_sh = off_gi + (size_t)NI * GF_GP * 4;
-  static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 15) & ~(size_t)15;
+  static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 127) & ~(size_t)127;  // quad blocks stay block-aligned
   static constexpr size_t off_bar = off_st + P::STAGE_BYTES;
   static constexpr size_t bytes = off_bar + 16;
 };
@@ -1074,11 +1112,11 @@ struct GfSmem {
 // One output row:   workers publish(yo) | bar A | aux scan(yo) || workers acc(row yin+1) | bar B |
 //                   aux TMA(row yin+2) || workers window sums + per-pixel work of yo | bar C
 template <class P>
-__global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
+__global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
   constexpr int NI = P::NI, ND = P::ND, NT = P::NT, GP = GF_GP;
   constexpr int NIa = NI > 0 ? NI : 1;
   typedef GfSmem<P> L;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* Pd01 = reinterpret_cast<double2*>(smem_raw);
   double2* Pd23 = reinterpret_cast<double2*>(smem_raw + L::off_d23);
   double* Gd = reinterpret_cast<double*>(smem_raw + L::off_gd);
@@ -1117,7 +1155,7 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
   const int tA = max(1, (gg.HL + 4 - xs) >> 2), tB = min(NQ, (gg.Wp - xs + gg.HL + 4) >> 2);
 
   // the quad-total rows are scanned over their whole length: keep the unused tail finite
-  for (int i = t; i < GP; i += NT + 32) {
+  for (int i = t; i < GP; i += NT + 32 * P::NAUX) {
 #pragma unroll
     for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
 #pragma unroll
@@ -1145,17 +1183,15 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
       if (yi >= y_end) return;
       const int yli = yi - 2 * r - 1;
       const bool en = (yi >= 0 && yi < H), le = (yli >= y_first);
-      const unsigned row_bytes = (unsigned)(tB - tA) * 16u;
-      const unsigned n_rows = (en ? P::NP : 0) + (le ? P::NP : 0);
-      mbar_arrive_expect_tx(mbar, n_rows * row_bytes);
+      // one bulk copy per row: (tB - tA) quads x NP chunks of 16 bytes, contiguous in the interleaved layout
+      const unsigned row_bytes = (unsigned)(tB - tA) * 16u * P::NP;
+      mbar_arrive_expect_tx(mbar, ((en ? 1u : 0u) + (le ? 1u : 0u)) * row_bytes);
       float4* stg = reinterpret_cast<float4*>(stage);
-      const int gxa = xs - gg.HL - 4 + 4 * tA;
-#pragma unroll 1
-      for (int k = 0; k < P::NP; k++) {
-        const float* pl = pol.plane(k);
-        if (en) tma_bulk_g2s(stg + k * NT + tA, pl + (size_t)yi * gg.Wp + gxa, row_bytes, mbar);
-        if (le) tma_bulk_g2s(stg + (P::NP + k) * NT + tA, pl + (size_t)yli * gg.Wp + gxa, row_bytes, mbar);
-      }
+      const int gqa = (xs - gg.HL - 4 + 4 * tA) >> 2;   // global quad index of strip quad tA
+      const float4* rows = reinterpret_cast<const float4*>(pol.coef_rows());
+      const size_t qpr = (size_t)(gg.Wp >> 2);
+      if (en) tma_bulk_g2s(stg + (size_t)tA * P::NP, rows + ((size_t)yi * qpr + gqa) * P::NP, row_bytes, mbar);
+      if (le) tma_bulk_g2s(stg + (size_t)(NT + tA) * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, mbar);
     }
   };
   // workers: add march row yi to the running sums and drop row yi - 2r - 1
@@ -1177,13 +1213,16 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
         if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gx);
       }
       cp_async_commit();
-      if (qload) {
-        if (enter) pol.template accum<+1>(curE, cmask, Vi, Vd);
-        if (leave) pol.template accum<-1>(curL, cmask, Vi, Vd);
+      if (cmask == 0xfu) {  // whole quad inside the image: straight-line code
+        if (enter) pol.template accum<+1, true>(curE, cmask, Vi, Vd);
+        if (leave) pol.template accum<-1, true>(curL, cmask, Vi, Vd);
+      } else if (qload) {
+        if (enter) pol.template accum<+1, false>(curE, cmask, Vi, Vd);
+        if (leave) pol.template accum<-1, false>(curL, cmask, Vi, Vd);
       }
     } else {
       mbar_wait(mbar, (unsigned)par);  // phase parity = march row parity
-      if (qload && (enter || leave)) gf_accum_staged<P::NP, NT>(reinterpret_cast<const float4*>(stage), enter, leave, cmask, Vd);
+      if (qload && (enter || leave)) gf_accum_staged<P::NP, NT>(reinterpret_cast<const float4*>(stage), gx >> 2, enter, leave, cmask, Vd);
     }
   };
 
@@ -1232,12 +1271,16 @@ __global__ void __launch_bounds__(P::NT + 32) __maxnreg__(P::MAXREG) gf_march_ke
     }
     __syncthreads();  // A
     if (aux) {
-      // prefix over the quad totals, four moments per round (8 lanes each)
-      const int seg = lane & 7, mq = lane >> 3;
+      // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
+      // the auxiliary warps
+      const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
+      constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
 #pragma unroll
-      for (int k0 = 0; k0 < NI; k0 += 4) gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI);
-#pragma unroll
-      for (int k0 = 0; k0 < ND; k0 += 4) gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND);
+      for (int rd = 0; rd < RI + RD; rd++) {
+        if (rd % P::NAUX != aw) continue;
+        if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
+        else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
+      }
     } else {
       acc(yin + 1);
     }
@@ -1374,7 +1417,7 @@ static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, 
     attr_done = true;
   }
   dim3 grid(strips, segs, n);
-  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT + 32, smem, gc, gg);
+  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT + 32 * P::NAUX, smem, gc, gg);
   return UWIP_OK;
 }
 
