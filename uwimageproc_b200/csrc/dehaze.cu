@@ -975,7 +975,7 @@ struct PolGF2a {
 
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
-  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 168, NT = 160, NAUX = 1;
+  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false;
   typedef ExpShared Shared;
   struct Raw {};
