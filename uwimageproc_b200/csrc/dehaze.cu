@@ -734,8 +734,8 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
-  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false;
+  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 192, NAUX = 1;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -820,7 +820,7 @@ struct PolGF1a {
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true;
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -907,7 +907,7 @@ struct PolGF1b {
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -984,7 +984,7 @@ struct PolGF2a {
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true;
   typedef ExpShared Shared;
   struct Raw {};
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1110,7 +1110,10 @@ struct GfSmem {
   static constexpr size_t off_gd = off_d23 + (size_t)ND * NT * 16;
   static constexpr size_t off_pi = off_gd + (size_t)ND * GF_GP * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
-  static constexpr size_t off_sh = off_gi + (size_t)NI * GF_GP * 4;
+  static constexpr size_t buf_bytes = (off_gi + (size_t)NI * GF_GP * 4 + 127) & ~(size_t)127;  // one published row
+  // DBUF: two copies addressed by the parity of the output row - the next row can be published while slow
+  // warps still read this one, which removes the third CTA barrier of a row
+  static constexpr size_t off_sh = buf_bytes * (P::DBUF ? 2 : 1);
   static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 127) & ~(size_t)127;  // quad blocks stay block-aligned
   static constexpr size_t off_bar = off_st + P::STAGE_BYTES;
   static constexpr size_t bytes = off_bar + 16;
@@ -1133,6 +1136,14 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   double* Gd = reinterpret_cast<double*>(smem_raw + L::off_gd);
   uint4* Pi = reinterpret_cast<uint4*>(smem_raw + L::off_pi);
   uint32_t* Gi = reinterpret_cast<uint32_t*>(smem_raw + L::off_gi);
+  auto select_buffer = [&](int yo) {  // published-row arrays of output row yo
+    unsigned char* b = smem_raw + ((P::DBUF && (yo & 1)) ? L::buf_bytes : 0);
+    Pd01 = reinterpret_cast<double2*>(b);
+    Pd23 = reinterpret_cast<double2*>(b + L::off_d23);
+    Gd = reinterpret_cast<double*>(b + L::off_gd);
+    Pi = reinterpret_cast<uint4*>(b + L::off_pi);
+    Gi = reinterpret_cast<uint32_t*>(b + L::off_gi);
+  };
   typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(smem_raw + L::off_sh);
   unsigned char* stage = smem_raw + L::off_st;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
@@ -1166,11 +1177,14 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   const int tA = max(1, (gg.HL + 4 - xs) >> 2), tB = min(NQ, (gg.Wp - xs + gg.HL + 4) >> 2);
 
   // the quad-total rows are scanned over their whole length: keep the unused tail finite
-  for (int i = t; i < GP; i += NT + 32 * P::NAUX) {
+  for (int bsel = 0; bsel < (P::DBUF ? 2 : 1); bsel++) {
+    select_buffer(bsel);
+    for (int i = t; i < GP; i += NT + 32 * P::NAUX) {
 #pragma unroll
-    for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
+      for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
 #pragma unroll
-    for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
+      for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
+    }
   }
   if constexpr (!P::PREFETCH) {
     if (t == NT) mbar_init(mbar, 1);
@@ -1265,6 +1279,7 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       continue;
     }
     // ---- publish the quad prefixes and totals -------------------------------------------------------
+    select_buffer(yo);
     if (qact) {
 #pragma unroll
       for (int k = 0; k < NI; k++) {
@@ -1383,7 +1398,7 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
         if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
       }
     }
-    __syncthreads();  // C
+    if constexpr (!P::DBUF) __syncthreads();  // C (with two buffers the barriers A, B of the next row order the reuse)
   }
   pol.finish();
 }
