@@ -734,8 +734,8 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
-  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 192, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
+  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = false;  // two row buffers of 17 moments do not fit beside 224 quads
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
