@@ -200,6 +200,9 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # the contract is ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
