@@ -326,3 +326,32 @@ def test_cpp_shims_on_device():
         subprocess.run(["bash", os.path.join(root, "uwimageproc_b200", "shims", "check.sh")], check=True, capture_output=True)
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("radius", [3, 4, 7, 10, 16, 40])
+def test_refined_transmission_other_radii(ctx, radius):
+    """The guided-filter radius is a parameter of the ABI (the reference fixes r=40, BGDehaze.py:41): radii that
+    are multiples of 4 take the quad path, the others the scalar window path; both against the oracle."""
+    fr = O.synth_frame(0x5EED0003, 2, 212, 118)   # width not a multiple of 4: pad columns are exercised too
+    normI = O.normalize_frame(fr)
+    for eps, tmin in [(1e-3, 0.2), (1e-2, 0.35)]:
+        rb, rg = ctx.refined_transmission(fr, ctx.dehaze_params(radius=radius, eps=eps, tmin=tmin))
+        tb, tg = O.refined_t(normI, 15, tmin, radius, eps)
+        assert (np.abs(rb - tb) / np.abs(tb)).max() < 1e-5, (radius, eps)
+        assert (np.abs(rg - tg) / np.abs(tg)).max() < 1e-5, (radius, eps)
+
+
+def test_dehaze_degenerate_frames(ctx):
+    """Constant frame (range 0: every normalised value is 0/0) and a two-level frame: the reference turns the
+    constant frame into NaN (imwrite stores zeros); the CUDA path must flag it and write zeros, not crash."""
+    const = np.full((64, 80, 3), 93, np.uint8)
+    out = ctx.bgdehaze(const)
+    assert out.shape == const.shape and out.max() == 0
+    two = const.copy()
+    two[:, 40:] = (30, 200, 120)
+    got = ctx.bgdehaze(two)
+    ref, ref8 = O.bgdehaze_frame(two, 15)
+    if np.isnan(ref).any():
+        assert got.max() == 0
+    else:
+        assert np.abs(got.astype(int) - ref8.astype(int)).max() <= 1
