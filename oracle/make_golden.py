@@ -103,6 +103,7 @@ def main():
         "hsv_crc": O.crc32(hsv),
         "hsv2bgr_crc": O.crc32(cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)),
         "ycrcb_crc": O.crc32(cv2.cvtColor(bgr, cv2.COLOR_BGR2YCrCb)),
+        "ycrcb2bgr_crc": O.crc32(cv2.cvtColor(cv2.cvtColor(bgr, cv2.COLOR_BGR2YCrCb), cv2.COLOR_YCrCb2BGR)),
     }
 
     # ---- exhaustive tables ------------------------------------------------------------
@@ -111,6 +112,7 @@ def main():
     allbgr = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
     kat["all_bgr2hsv_crc"] = O.crc32(cv2.cvtColor(allbgr, cv2.COLOR_BGR2HSV))
     kat["all_bgr2ycrcb_crc"] = O.crc32(cv2.cvtColor(allbgr, cv2.COLOR_BGR2YCrCb))
+    kat["all_ycrcb2bgr_crc"] = O.crc32(cv2.cvtColor(allbgr, cv2.COLOR_YCrCb2BGR))  # the same 2^24 triples read as Y,Cr,Cb
     g = np.arange(180 * 65536, dtype=np.uint32)
     allhsv = np.stack([(g >> 16), (g >> 8) & 255, g & 255], axis=-1).astype(np.uint8).reshape(180 * 64, 1024, 3)
     kat["all_hsv2bgr_trunc_crc"] = O.crc32(cv2.cvtColor(allhsv, cv2.COLOR_HSV2BGR))
@@ -235,6 +237,15 @@ def main():
             "chain_crc": O.crc32(O.bgdehaze_frame(b_cv, 15)[1]),
         }
     kat["chain"] = chain
+    # ---- histretch on the YCrCb letters with cv2 doing the conversions (histretch.cpp:232-240, intended order)
+    ycx = {}
+    fr = O.synth_frame(0x5EED0001, 2, 479, 321)
+    for letter, ch in (("Y", 0), ("C", 1), ("X", 2)):
+        d = cv2.cvtColor(fr, cv2.COLOR_BGR2YCrCb)
+        d[..., ch] = O.img_channel_stretch(np.ascontiguousarray(d[..., ch]), 2, 98)
+        ycx[letter] = O.crc32(cv2.cvtColor(d, cv2.COLOR_YCrCb2BGR))
+    ycx["literal"] = O.crc32(cv2.cvtColor(cv2.cvtColor(fr, cv2.COLOR_BGR2YCrCb), cv2.COLOR_YCrCb2BGR))
+    kat["histretch_ycrcb"] = ycx
     kat["synth_1080p_f0_crc"] = O.crc32(O.synth_frame(0x5EED0003, 0, 1920, 1080))
 
     with open(os.path.join(GOLD, "kat.json"), "w") as f:

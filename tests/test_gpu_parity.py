@@ -59,11 +59,13 @@ def test_stretch_edge_cases(ctx, kat):
 def test_histretch_frame(ctx, shape):
     h, w = shape
     for fr in (O.synth_frame(0x5EED0001, 2, w, h), rand_frame(h + w, h, w)):
-        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r"]:
+        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r", "Y", "C", "X", "YV", "CX"]:
             got = ctx.histretch(fr, ch, 2, 98)
             assert (got == O.histretch_frame(fr, ch, 2, 98)).all(), (shape, ch)
         got = ctx.histretch(fr, "V", 1, 99, order="literal")
         assert (got == O.histretch_frame(fr, "V", 1, 99, order="literal")).all()
+        got = ctx.histretch(fr, "Y", 1, 99, order="literal")
+        assert (got == O.histretch_frame(fr, "Y", 1, 99, order="literal")).all()
         for mode in ["trunc", "rint"]:
             assert (ctx.histretch(fr, "V", 1, 99, hsv_round=mode) == O.histretch_frame(fr, "V", 1, 99, hsv_rounding=mode)).all()
 
@@ -72,7 +74,7 @@ def test_histretch_unsupported_letters(ctx):
     import uwimageproc_b200 as u
 
     fr = rand_frame(1, 16, 16)
-    for ch in ["h", "L", "Y"]:
+    for ch in ["h", "L", "a"]:
         with pytest.raises(u.UwipError) as e:
             ctx.histretch(fr, ch)
         assert e.value.status == -3

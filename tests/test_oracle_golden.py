@@ -71,6 +71,15 @@ def test_k2_conversions(kat):
     assert O.crc32(hsv) == kat["K2"]["hsv_crc"] == "0ff6a727"
     assert O.crc32(O.hsv2bgr(hsv)) == kat["K2"]["hsv2bgr_crc"] == "46d8170b"
     assert O.crc32(O.bgr2ycrcb(bgr)) == kat["K2"]["ycrcb_crc"] == "249772e2"
+    assert O.crc32(O.ycrcb2bgr(O.bgr2ycrcb(bgr))) == kat["K2"]["ycrcb2bgr_crc"]
+
+
+def test_histretch_ycrcb_letters(kat):
+    """Y, C, X letters (histretch.cpp:155-156, transformation[3]); goldens made with cv2 doing the conversions."""
+    fr = O.synth_frame(0x5EED0001, 2, 479, 321)
+    for letter in "YCX":
+        assert O.crc32(O.histretch_frame(fr, letter, 2, 98)) == kat["histretch_ycrcb"][letter]
+    assert O.crc32(O.histretch_frame(fr, "X", 2, 98, order="literal")) == kat["histretch_ycrcb"]["literal"]
 
 
 def test_exhaustive_colour_tables(kat):
@@ -78,6 +87,7 @@ def test_exhaustive_colour_tables(kat):
     allbgr = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
     assert O.crc32(O.bgr2hsv(allbgr)) == kat["all_bgr2hsv_crc"]
     assert O.crc32(O.bgr2ycrcb(allbgr)) == kat["all_bgr2ycrcb_crc"]
+    assert O.crc32(O.ycrcb2bgr(allbgr)) == kat["all_ycrcb2bgr_crc"]
     g = np.arange(180 * 65536, dtype=np.uint32)
     allhsv = np.stack([(g >> 16), (g >> 8) & 255, g & 255], axis=-1).astype(np.uint8).reshape(180 * 64, 1024, 3)
     assert O.crc32(O.hsv2bgr(allhsv, "cv2")) == kat["all_hsv2bgr_trunc_crc"]

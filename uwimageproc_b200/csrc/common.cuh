@@ -163,7 +163,7 @@ __host__ __device__ inline double dunkey(unsigned long long k) {
 __device__ __forceinline__ int hsv_sdiv(int i) { return i ? ((255 << 12) * 2 + i) / (2 * i) : 0; }
 __device__ __forceinline__ int hsv_hdiv(int i) { return i ? (2 * 122880 + i) / (2 * i) : 0; }
 
-enum Channel { CH_B = 0, CH_G = 1, CH_R = 2, CH_H = 3, CH_S = 4, CH_V = 5 };
+enum Channel { CH_B = 0, CH_G = 1, CH_R = 2, CH_H = 3, CH_S = 4, CH_V = 5, CH_Y = 6, CH_CR = 7, CH_CB = 8 };
 
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
@@ -235,6 +235,18 @@ __device__ __forceinline__ void bgr2ycrcb_u8(int b, int g, int r, int& Y, int& C
   Cb = ((b - Y) * 9241 + 128 * 16384 + 8192) >> 14;
   Cr = min(max(Cr, 0), 255);
   Cb = min(max(Cb, 0), 255);
+}
+
+// cvtColor(YCrCb2BGR) 8-bit: integer, shift 14, saturating (equal to cv2 4.13.0 on all 2^24 triples,
+// tests/golden/kat.json: all_ycrcb2bgr_crc).
+__device__ __forceinline__ void ycrcb2bgr_u8(int Y, int Cr, int Cb, int& b, int& g, int& r) {
+  Cr -= 128; Cb -= 128;
+  b = Y + ((Cb * 29049 + 8192) >> 14);
+  g = Y + ((Cb * -5636 + Cr * -11698 + 8192) >> 14);
+  r = Y + ((Cr * 22987 + 8192) >> 14);
+  b = min(max(b, 0), 255);
+  g = min(max(g, 0), 255);
+  r = min(max(r, 0), 255);
 }
 
 // saturate_cast<uchar>(cvRound(x)) : NaN / inf -> INT_MIN -> 0

@@ -40,6 +40,11 @@ __device__ __forceinline__ int extract_channel(int b, int g, int r, const int* s
   if (CH == CH_G) return g;
   if (CH == CH_R) return r;
   if (CH == CH_V) return imax3(b, g, r);
+  if (CH == CH_Y || CH == CH_CR || CH == CH_CB) {
+    int Y, Cr, Cb;
+    bgr2ycrcb_u8(b, g, r, Y, Cr, Cb);
+    return CH == CH_Y ? Y : (CH == CH_CR ? Cr : Cb);
+  }
   int h, s, v;
   bgr2hsv_u8(b, g, r, sdiv, hdiv, h, s, v);
   return CH == CH_H ? h : s;
@@ -142,6 +147,9 @@ int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n, int w, int h, 
     case CH_H: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_H>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
     case CH_S: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_S>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
     case CH_V: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_V>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
+    case CH_Y: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_Y>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
+    case CH_CR: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CR>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
+    case CH_CB: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CB>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
   return UWIP_OK;
@@ -256,6 +264,17 @@ __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint
   if (CH == CH_B) { if (use_lut) b = s_lut[b]; return; }
   if (CH == CH_G) { if (use_lut) g = s_lut[g]; return; }
   if (CH == CH_R) { if (use_lut) r = s_lut[r]; return; }
+  if (CH == CH_Y || CH == CH_CR || CH == CH_CB) {  // transformation[3]: BGR2YCrCb / YCrCb2BGR (histretch.cpp:155-156)
+    int Y, Cr, Cb;
+    bgr2ycrcb_u8(b, g, r, Y, Cr, Cb);
+    if (use_lut) {
+      if (CH == CH_Y) Y = s_lut[Y];
+      if (CH == CH_CR) Cr = s_lut[Cr];
+      if (CH == CH_CB) Cb = s_lut[Cb];
+    }
+    ycrcb2bgr_u8(Y, Cr, Cb, b, g, r);
+    return;
+  }
   int h, s, v;
   bgr2hsv_u8(b, g, r, sdiv, hdiv, h, s, v);
   if (use_lut) {
@@ -324,6 +343,9 @@ int k_apply_lut_frame(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
     case CH_H: AL(CH_H); break;
     case CH_S: AL(CH_S); break;
     case CH_V: AL(CH_V); break;
+    case CH_Y: AL(CH_Y); break;
+    case CH_CR: AL(CH_CR); break;
+    case CH_CB: AL(CH_CB); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
 #undef AL
@@ -419,6 +441,9 @@ static int letter_channel(char c) {
     case 'H': return CH_H;
     case 'S': return CH_S;
     case 'V': return CH_V;
+    case 'Y': return CH_Y;
+    case 'C': return CH_CR;
+    case 'X': return CH_CB;
   }
   return -1;
 }
@@ -434,12 +459,12 @@ int histretch_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, in
   for (const char* c = channels; *c; ++c) {
     int sp = uwip_num_space(*c);
     if (sp == -1) continue;  // "Option not recognized, skipping..."
-    if (sp >= 2) {
+    if (sp == 2 || sp == 3) {  // HLS, Lab
       uwip_set_err(ctx, "channel letter '%c' (colour space %d) is not built yet (SURVEY 8f N2)", *c, sp);
       return UWIP_ERR_UNSUPPORTED;
     }
     int ch = letter_channel(*c);
-    bool literal_hsv = (sp == 1 && order == UWIP_ORDER_LITERAL);
+    bool literal_hsv = (sp != 0 && order == UWIP_ORDER_LITERAL);  // literal order: the frame becomes its colour-space round trip
     if (!literal_hsv) {
       UWIP_CHECK(k_histogram_frame(ctx, cur, n, w, h, ch, d_hist));
       UWIP_CHECK(k_percentile_lut(ctx, d_hist, n, w, h, lo, hi, nullptr, d_lut));
