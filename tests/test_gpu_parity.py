@@ -140,6 +140,16 @@ def test_synth_matches_oracle(ctx, kat):
 
 
 # ---- bgdehaze ------------------------------------------------------------------------------------------
+# Tolerance of the FINAL float map: 1 LSB of the 8-bit output (1/255), the same bar as the bytes.  The
+# continuous stages before it are held to 1e-5; adaptiveExp_map itself is discontinuous in them:
+# `(restored*255).astype(uint8)` (BGDehaze.py:75) truncates, and the red channel of `restored` is
+# (k' - rmin)/(rmax - rmin) mathematically, i.e. EXACTLY on an integer boundary times 1/255 for every pixel when
+# rmax - rmin = 255 - which side it falls on is decided by the last bits of mean(Jb), mean(Jg) (a numpy pairwise
+# sum in the reference).  One flipped byte at the extreme of the YCrCb images moves the joint min-max
+# normalisation by one level (0.3-0.4 %), which stays inside 1 LSB of the output but not inside 2e-4.
+OUT_TOL = 1.0 / 255.0
+
+
 def _dehaze_case(ctx, fr, tag):
     st = {}
     out, out8 = O.bgdehaze_frame(fr, 15, st)
@@ -157,7 +167,7 @@ def _dehaze_case(ctx, fr, tag):
     rest = ctx.rc_correction(fr)
     assert np.abs(rest - st["restored"]).max() < 1e-5, tag
     got8, gotf = ctx.bgdehaze(fr, return_float=True)
-    assert np.abs(gotf - out).max() < 2e-4, tag
+    assert np.abs(gotf - out).max() < OUT_TOL, tag
     d = np.abs(got8.astype(int) - out8.astype(int))
     assert d.max() <= 1, (tag, d.max())  # max abs <= 1 LSB on the 8-bit output
     return (d > 0).mean()
@@ -178,7 +188,7 @@ def test_dehaze_golden_literal(ctx):
         B, _ = ctx.background_light(fr, 15)
         assert np.abs(B - z[name + "/B"]).max() < 1e-15
         got8, gotf = ctx.bgdehaze(fr, return_float=True)
-        assert np.abs(gotf - z[name + "/out"]).max() < 2e-4, name
+        assert np.abs(gotf - z[name + "/out"]).max() < OUT_TOL, name
         ref8 = O._sat_u8_from_rint(z[name + "/out"] * 255).astype(int)
         assert np.abs(got8.astype(int) - ref8).max() <= 1, name
         if name + "/t_blue" in z.files:
@@ -357,3 +367,26 @@ def test_dehaze_degenerate_frames(ctx):
         assert got.max() == 0
     else:
         assert np.abs(got.astype(int) - ref8.astype(int)).max() <= 1
+
+
+def test_result_independent_of_batch_split(ctx):
+    """A frame's bytes must not depend on how the batch is cut (sub-batches, vertical segments of the guided
+    filter march, GPU count): every value entering a running sum sits on a power-of-two grid, so the sums are
+    exact.  1080p frames alone (many vertical segments) against the same frames inside a batch of 12 (one)."""
+    import torch
+
+    W, H, n = 1920, 1080, 12
+    d_in = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(d_in, 0x5EED0006, 0, n, W, H)
+    d_out = torch.empty_like(d_in)
+    ctx.chain_dev(d_in, d_out, n, W, H)
+    ctx.synchronize()
+    whole = ctx.checksum_dev(d_out, n, W, H)
+    for i in (0, 5, 11):
+        one = torch.empty_like(d_in[i:i + 1])
+        ctx.chain_dev(d_in[i:i + 1].contiguous(), one, 1, W, H)
+        ctx.synchronize()
+        assert ctx.checksum_dev(one, 1, W, H)[0] == whole[i], i
+    # host-buffer path (ramped sub-batches) == device path
+    host = ctx.chain(d_in.cpu().numpy())
+    assert (host == d_out.cpu().numpy()).all()

@@ -66,6 +66,16 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
+// Round to a multiple of 2^-G (round-half-even) by the add/subtract of 1.5*2^(52-G); valid for |x| < 2^(51-G).
+// Every value that enters a running sum is put on such a grid: the vertical running sums (add the entering
+// row, subtract the leaving row) are then EXACT in fp64, so the result of a frame does not depend on where a
+// CTA's vertical segment starts - i.e. not on the batch size, the sub-batch split or the GPU count.
+template <int G>
+__device__ __forceinline__ double grid_round(double x) {
+  const double M = 6755399441055744.0 / (double)(1ull << G);  // 1.5 * 2^(52-G)
+  return (x + M) - M;
+}
+
 // cp.async (LDGSTS): global -> shared without a register in between
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
   unsigned a = (unsigned)__cvta_generic_to_shared(smem);
@@ -521,6 +531,11 @@ __device__ __forceinline__ void gf_solve(const double* A, double rdet, const dou
   b = (Sp - a[0] * Sd[0] - a[1] * Sd[1] - a[2] * Sd[2]) * invN;
 }
 
+// one coefficient chunk (a0, a1, a2, b) as stored: on the 2^-34 grid (absolute step 6e-11), then f32
+__device__ __forceinline__ float4 coef_pack(const double* a, double b) {
+  return make_float4((float)grid_round<34>(a[0]), (float)grid_round<34>(a[1]), (float)grid_round<34>(a[2]), (float)grid_round<34>(b));
+}
+
 struct GfCommon {
   const uint32_t* kq;     // [n][H][Wp] packed k'_b k'_g k'_r m'_b
   const uint8_t* mg;      // [n][H][Wp] m'_g
@@ -756,7 +771,7 @@ struct PolGF1a {
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
       int c = i >> 8, k = i & 255;
       double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
-      sh->pT[c][k] = (t < g.tmin) ? g.tmin : t;              // np.maximum(t, tmin) (NaN stays NaN)
+      sh->pT[c][k] = grid_round<28>((t < g.tmin) ? g.tmin : t);  // np.maximum(t, tmin) (NaN stays NaN), on the 2^-28 grid
     }
     epsN_k = g.eps * range * range;
     __syncthreads();
@@ -809,9 +824,9 @@ struct PolGF1a {
     const int gq = x >> 2, c = x & 3;
     float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 8;
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
-    blk[coef_chunk<8>(gq, c, 0)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
+    blk[coef_chunk<8>(gq, c, 0)] = coef_pack(a, b);
     gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
-    blk[coef_chunk<8>(gq, c, 1)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
+    blk[coef_chunk<8>(gq, c, 1)] = coef_pack(a, b);
   }
   __device__ __forceinline__ void store_pair(int, int) {}
   __device__ void finish() {}
@@ -972,7 +987,7 @@ struct PolGF2a {
     gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 1, a, b);
     const int gq = x >> 2;
     float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 4;
-    blk[coef_chunk<4>(gq, x & 3, 0)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)b);
+    blk[coef_chunk<4>(gq, x & 3, 0)] = coef_pack(a, b);
   }
   __device__ __forceinline__ void store_pair(int, int) {}
   __device__ void finish() {
@@ -1528,7 +1543,7 @@ __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) 
       // pad columns hold zeros: keep them away from the table (their S is never used)
       bool pad = (w & 255u) < a || (w >> 24) < b;
       w -= ysub;
-      o[c] = pad ? 0.f : (float)__ldg(stab + (((w & 255u) << 8) | (w >> 24)));
+      o[c] = pad ? 0.f : (float)grid_round<28>(__ldg(stab + (((w & 255u) << 8) | (w >> 24))));
     }
     reinterpret_cast<float4*>(sp)[qi] = make_float4(o[0], o[1], o[2], o[3]);
   }
