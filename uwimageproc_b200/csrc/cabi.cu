@@ -550,21 +550,20 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
   return UWIP_OK;
 }
 
-// Sub-batch schedule of the host-buffer chain: small batches at both ends (only the first upload and the
-// last download are not hidden behind compute, so they should be short), doubling towards `nb_max` in
-// between.  PCIe moves a 4K frame about 2.4x faster than the chain processes it, so a doubling ramp never
-// starves the compute stream.
-static std::vector<int> e2e_schedule(int n, int nb_max) {
-  std::vector<int> head;
-  int used = 0;
-  for (int c = 8; c <= nb_max && used + c <= n / 2; c *= 2) { head.push_back(c); used += c; }
-  std::vector<int> sizes(head);
-  int mid = n - 2 * used;
-  if (mid > 0) {
-    int parts = (mid + nb_max - 1) / nb_max;
-    for (int i = 0; i < parts; i++) sizes.push_back(mid / parts + (i < mid % parts ? 1 : 0));
-  }
-  for (auto it = head.rbegin(); it != head.rend(); ++it) sizes.push_back(*it);
+// Sub-batch schedule of the host-buffer chain.  Only the first upload and the last download are not hidden
+// behind compute, so the first and last sub-batches are short; every sub-batch is a multiple of the
+// "wave" u (frames whose guided-filter strips fill the SMs exactly once) so that no launch ends in a
+// nearly empty wave.  PCIe moves a 4K frame about 2.4x faster than the chain processes it, so going from
+// u to 2u never starves the compute stream.
+static std::vector<int> e2e_schedule(int n, int nb_max, int u) {
+  std::vector<int> sizes;
+  u = std::max(1, std::min(u, nb_max));
+  int big = std::max(u, std::min(2 * u, nb_max) / u * u);
+  int rem = n;
+  if (rem > 0) { int m = std::min(u, rem); sizes.push_back(m); rem -= m; }
+  while (rem > big + u) { sizes.push_back(big); rem -= big; }
+  if (rem > u) { sizes.push_back(rem - u); rem = u; }
+  if (rem > 0) sizes.push_back(rem);
   return sizes;
 }
 
@@ -575,7 +574,7 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   UWIP_CHECK(chain_check(ctx, p, n, w, h));
   int nb = sub_batch(n, w, h);
   nb = std::max(1, std::min(nb, (n + 1) / 2));  // at least two sub-batches so copies overlap compute
-  std::vector<int> sizes = e2e_schedule(n, nb);
+  std::vector<int> sizes = e2e_schedule(n, nb, dehaze_wave_frames(ctx, w));
   nb = *std::max_element(sizes.begin(), sizes.end());
   FrameState* fs = frame_state_get(ctx, nb);
   int32_t* flags = flags_get(ctx, n);

@@ -299,6 +299,7 @@ struct DehazeDebug {  // optional float64 stage outputs for the stage-wise host 
 };
 int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, const uwip_dehaze_params& p, bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags = nullptr);
 int frame_state_reset(uwip_ctx* ctx, FrameState* fs, int n);
+int dehaze_wave_frames(const uwip_ctx* ctx, int w);  // frames whose guided-filter strips fill the SMs exactly once
 FrameState* frame_state_get(uwip_ctx* ctx, int n);
 
 // synth.cu

@@ -1605,6 +1605,13 @@ __global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, in
 // -------------------------------------------------------------------------------------------------
 // driver
 // -------------------------------------------------------------------------------------------------
+// Batch size for which the strips of the one-CTA-per-SM marches make one full wave (4K: 148 SMs / 5 strips =
+// 29 frames); the host-buffer pipeline cuts its sub-batches in multiples of it.
+int dehaze_wave_frames(const uwip_ctx* ctx, int w) {
+  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40, PolGF1a::NT);
+  return std::max(1, ctx->sm_count / cdiv(w, g.SW));
+}
+
 int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const uwip_dehaze_params& p,
                       bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags) {
   UWIP_REQUIRE(ctx, n >= 1 && W >= 1 && H >= 1, "bad size");
