@@ -750,7 +750,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = false;  // two row buffers of 17 moments do not fit beside 224 quads
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -1116,13 +1116,14 @@ __device__ __forceinline__ void gf_scan_task(T* row, int seg, bool live) {
 
 // shared-memory layout of one published row; every pitch is a compile-time constant so that each
 // access is base register + immediate:
-//   Pd01 [ND][NT] double2 (prefix 0,1 of the quad) | Pd23 [ND][NT] double2 (prefix 2,3)
+//   Pd01 [ND][NT] double2 (prefix 0,1 of the quad) | Pd2 [ND][NT] f64 (prefix 2; prefix 3 = the quad total
+//   is the difference of two neighbouring entries of the scanned totals and is not stored)
 //   Gd [ND][GF_GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GF_GP] u32 | policy tables | row staging | mbarrier
 template <class P>
 struct GfSmem {
   static constexpr int NT = P::NT, NI = P::NI, ND = P::ND;
   static constexpr size_t off_d23 = (size_t)ND * NT * 16;
-  static constexpr size_t off_gd = off_d23 + (size_t)ND * NT * 16;
+  static constexpr size_t off_gd = off_d23 + (size_t)ND * NT * 8;
   static constexpr size_t off_pi = off_gd + (size_t)ND * GF_GP * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t buf_bytes = (off_gi + (size_t)NI * GF_GP * 4 + 127) & ~(size_t)127;  // one published row
@@ -1147,14 +1148,14 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   typedef GfSmem<P> L;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* Pd01 = reinterpret_cast<double2*>(smem_raw);
-  double2* Pd23 = reinterpret_cast<double2*>(smem_raw + L::off_d23);
+  double* Pd2 = reinterpret_cast<double*>(smem_raw + L::off_d23);
   double* Gd = reinterpret_cast<double*>(smem_raw + L::off_gd);
   uint4* Pi = reinterpret_cast<uint4*>(smem_raw + L::off_pi);
   uint32_t* Gi = reinterpret_cast<uint32_t*>(smem_raw + L::off_gi);
   auto select_buffer = [&](int yo) {  // published-row arrays of output row yo
     unsigned char* b = smem_raw + ((P::DBUF && (yo & 1)) ? L::buf_bytes : 0);
     Pd01 = reinterpret_cast<double2*>(b);
-    Pd23 = reinterpret_cast<double2*>(b + L::off_d23);
+    Pd2 = reinterpret_cast<double*>(b + L::off_d23);
     Gd = reinterpret_cast<double*>(b + L::off_gd);
     Pi = reinterpret_cast<uint4*>(b + L::off_pi);
     Gi = reinterpret_cast<uint32_t*>(b + L::off_gi);
@@ -1306,7 +1307,7 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       for (int k = 0; k < ND; k++) {
         double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
         Pd01[k * NT + t] = make_double2(p0, p1);
-        Pd23[k * NT + t] = make_double2(p2, p3);
+        Pd2[k * NT + t] = p2;
         Gd[k * GP + t] = p3;
       }
     }
@@ -1374,30 +1375,30 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
         if (gg.fast) {
 #pragma unroll
           for (int k = 0; k < ND; k++) {
-            double Wq = Gd[k * GP + thi - 1] - Gd[k * GP + tlo - 1];
+            const double Gl = Gd[k * GP + tlo - 1];
+            double Wq = Gd[k * GP + thi - 1] - Gl;
             double2 a01 = Pd01[k * NT + tlo];
             if (h == 0) {
               double2 b = Pd01[k * NT + thi];
               sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a01.x) + b.y;
             } else {
-              double a2 = Pd23[k * NT + tlo].x;
-              double2 b = Pd23[k * NT + thi];
-              sd[0][k] = (Wq - a01.y) + b.x; sd[1][k] = (Wq - a2) + b.y;
+              double a2 = Pd2[k * NT + tlo], b2 = Pd2[k * NT + thi];
+              sd[0][k] = (Wq - a01.y) + b2;
+              sd[1][k] = (Gd[k * GP + thi] - Gl) - a2;  // the whole quad thi is inside: totals up to and including it
             }
           }
         } else {
           const double* P01 = reinterpret_cast<const double*>(Pd01);
-          const double* P23 = reinterpret_cast<const double*>(Pd23);
 #pragma unroll
           for (int cc = 0; cc < 2; cc++) {
             int c = 2 * h + cc;
             int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
 #pragma unroll
             for (int k = 0; k < ND; k++) {
-              // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd23
+              // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd2
               int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-              double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : P23[(k * NT + (zl >> 2)) * 2]);
-              double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : P23[(k * NT + (zh >> 2)) * 2]);
+              double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : Pd2[k * NT + (zl >> 2)]);
+              double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : Pd2[k * NT + (zh >> 2)]);
               sd[cc][k] = (Gd[k * GP + (zh >> 2) - 1] + ph) - (Gd[k * GP + (zl >> 2) - 1] + pl);
             }
           }
