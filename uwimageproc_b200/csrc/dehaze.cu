@@ -1332,7 +1332,6 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
     }
     // ---- window sums and the per-pixel work -----------------------------------------------------------
     if (oact) {
-      const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
       pol.row_begin(yo, gx);
       // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
       // that trade loads for registers (INT_HALF) - two columns per half
@@ -1407,7 +1406,9 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
         for (int cc = 0; cc < 2; cc++) {
           int x = gx + 2 * h + cc;
           if (x < W) {
-            int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
+            // window pixel count, formed where it is used (a value kept across the loads above ends up in a spill slot)
+            const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
+            const int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
             pol.column(cc, yo, x, ny * nx, si[P::INT_HALF ? cc : 2 * h + cc], sd[cc]);
           }
         }
