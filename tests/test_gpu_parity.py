@@ -390,3 +390,35 @@ def test_result_independent_of_batch_split(ctx):
     # host-buffer path (ramped sub-batches) == device path
     host = ctx.chain(d_in.cpu().numpy())
     assert (host == d_out.cpu().numpy()).all()
+
+
+def test_abi_error_statuses(ctx):
+    """What the reference leaves undefined (preprocessing.h:60-64) or prints-and-skips becomes a status code."""
+    import ctypes as C
+
+    import uwimageproc_b200 as u
+
+    lib = ctx.lib
+    plane = np.zeros((16, 16), np.uint8)
+    out = np.zeros_like(plane)
+    hist = (C.c_float * 256)()
+    # null pointers, bad sizes, pitch smaller than a row
+    assert lib.uwip_histogram_u8(ctx.h, None, 16, 16, 16, hist) == -1
+    assert lib.uwip_histogram_u8(ctx.h, plane.ctypes.data, 0, 16, 16, hist) == -1
+    assert lib.uwip_histogram_u8(ctx.h, plane.ctypes.data, 16, 16, 8, hist) == -1
+    assert b"pitch" in lib.uwip_last_error(ctx.h) or b"bad image" in lib.uwip_last_error(ctx.h)
+    # percentiles outside 0 <= lo < hi <= 100
+    for lo, hi in [(-1, 50), (50, 50), (60, 40), (0, 101)]:
+        assert lib.uwip_channel_stretch_u8(ctx.h, plane.ctypes.data, 16, out.ctypes.data, 16, 16, 16, lo, hi, None, None) == -1
+    # dehaze parameter ranges
+    fr = np.zeros((32, 32, 3), np.uint8) + np.arange(32, dtype=np.uint8)[None, :, None] * 7
+    for kw in (dict(window=0), dict(window=35), dict(radius=0), dict(radius=161)):
+        with pytest.raises(u.UwipError) as e:
+            ctx.bgdehaze(fr, ctx.dehaze_params(**kw))
+        assert e.value.status == -1
+    # a call after an error works (the context stays usable)
+    assert (ctx.histogram(plane) == O.get_histogram(plane)).all()
+    # frame flags: asking for more frames than the last call processed is refused
+    ctx.chain(fr[None])
+    with pytest.raises(u.UwipError):
+        ctx.last_frame_flags(5)
