@@ -57,6 +57,36 @@ def cv_stretch(ch, lo, hi):
     return low, high, y, z
 
 
+def hls_goldens(kat):
+    """HLS letters h, s, l of histretch (transformation[1], histretch.cpp:155-156): cv2 does every conversion."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8)
+    body = trip.reshape(4096, 4096, 3)  # W % 8 == 0: every pixel through the vector body
+    tail = trip[: 7 * ((1 << 24) // 7)].reshape(-1, 7, 3)  # W < 8: every pixel through the scalar tail
+    hls = {
+        "all_bgr2hls_body_crc": O.crc32(cv2.cvtColor(body, cv2.COLOR_BGR2HLS)),
+        "all_bgr2hls_tail7_crc": O.crc32(cv2.cvtColor(tail, cv2.COLOR_BGR2HLS)),
+        # the same 2^24 triples read as (H, L, S), H up to 255 (a stretched H plane can hold that)
+        "all_hls2bgr_body_crc": O.crc32(cv2.cvtColor(body, cv2.COLOR_HLS2BGR)),
+        "all_hls2bgr_tail7_crc": O.crc32(cv2.cvtColor(tail, cv2.COLOR_HLS2BGR)),
+    }
+    letters = {}
+    for (W, H) in ((479, 321), (640, 360)):
+        fr = O.synth_frame(0x5EED0001, 2, W, H)
+        e = {}
+        for letter, ch in (("h", 0), ("s", 1), ("l", 2)):
+            d = cv2.cvtColor(fr, cv2.COLOR_BGR2HLS)
+            d[..., ch] = O.img_channel_stretch(np.ascontiguousarray(d[..., ch]), 2, 98)
+            e[letter] = O.crc32(cv2.cvtColor(d, cv2.COLOR_HLS2BGR))
+        e["literal"] = O.crc32(cv2.cvtColor(cv2.cvtColor(fr, cv2.COLOR_BGR2HLS), cv2.COLOR_HLS2BGR))
+        letters["%dx%d" % (W, H)] = e
+    hls["histretch"] = letters
+    bgr = np.random.default_rng(1).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    hls["K2_hls_crc"] = O.crc32(cv2.cvtColor(bgr, cv2.COLOR_BGR2HLS))
+    hls["K2_hls2bgr_crc"] = O.crc32(cv2.cvtColor(cv2.cvtColor(bgr, cv2.COLOR_BGR2HLS), cv2.COLOR_HLS2BGR))
+    kat["hls"] = hls
+
+
 def main():
     kat = {"cv2": cv2.__version__, "numpy": np.__version__}
 
@@ -247,6 +277,7 @@ def main():
     ycx["literal"] = O.crc32(cv2.cvtColor(cv2.cvtColor(fr, cv2.COLOR_BGR2YCrCb), cv2.COLOR_YCrCb2BGR))
     kat["histretch_ycrcb"] = ycx
     kat["synth_1080p_f0_crc"] = O.crc32(O.synth_frame(0x5EED0003, 0, 1920, 1080))
+    hls_goldens(kat)
 
     with open(os.path.join(GOLD, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1, sort_keys=True)
@@ -254,4 +285,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-hls" in sys.argv:  # add the HLS vectors to an existing kat.json without re-running the rest
+        path = os.path.join(GOLD, "kat.json")
+        with open(path) as f:
+            kat = json.load(f)
+        hls_goldens(kat)
+        with open(path, "w") as f:
+            json.dump(kat, f, indent=1, sort_keys=True)
+    else:
+        main()

@@ -235,6 +235,77 @@ def ycrcb2bgr(ycc: np.ndarray) -> np.ndarray:
     return np.stack([b, g, r], axis=-1).astype(np.uint8)
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64, one rounding at the end."""
+    return (a.astype(np.float64) * b.astype(np.float64) + np.asarray(c, dtype=np.float64)).astype(np.float32)
+
+
+def bgr2hls(bgr: np.ndarray, simd: str = "cv2") -> np.ndarray:
+    """cvtColor(COLOR_BGR2HLS) on 8UC3 (H in [0,180), order H, L, S): float32 arithmetic on k/255.
+    cv2 4.13.0 here runs the first 8*floor(W/8) pixels of every row through a vector body and the rest through
+    the scalar tail; the two differ in two places (found by fitting against all 2^24 triples, make_golden.py):
+      body: S denominator 2 - (vmax + vmin); `h += 360` fused with the product (one rounding)
+      tail: S denominator (2 - vmax) - vmin;  `h += 360` on the rounded value
+    In both, `(x - y)*d + 120|240` is one fused multiply-add.  simd='cv2': body/tail split; 'scalar': tail model
+    everywhere (what the C++ source says without vectorisation)."""
+    f32 = np.float32
+    b = bgr[..., 0].astype(f32) * f32(1 / 255.0)
+    g = bgr[..., 1].astype(f32) * f32(1 / 255.0)
+    r = bgr[..., 2].astype(f32) * f32(1 / 255.0)
+    vmax = np.maximum(np.maximum(b, g), r)
+    vmin = np.minimum(np.minimum(b, g), r)
+    diff = vmax - vmin
+    vs = vmax + vmin
+    lum = vs * f32(0.5)
+    W = bgr.shape[-2]
+    body = np.zeros(bgr.shape[:-1], bool)
+    if simd == "cv2":
+        body[..., : 8 * (W // 8)] = True
+    with np.errstate(all="ignore"):
+        den = np.where(body, f32(2) - vs, (f32(2) - vmax) - vmin)
+        sat = np.where(lum < f32(0.5), diff / vs, diff / den)
+        dinv = f32(60.0) / diff
+
+        def hsel(d1, d2, add):
+            hh = (d1 - d2) * dinv if add == 0 else _fma32(d1 - d2, dinv, add)
+            wrapped = np.where(body, _fma32(d1 - d2, dinv, add + 360.0), hh + f32(360.0))
+            return np.where(hh < 0, wrapped, hh)
+
+        hue = np.where(vmax == r, hsel(g, b, 0), np.where(vmax == g, hsel(b, r, 120.0), hsel(r, g, 240.0)))
+    gray = diff <= np.finfo(np.float32).eps
+    hue = np.where(gray, f32(0), hue)
+    sat = np.where(gray, f32(0), sat)
+    H = np.clip(np.rint(hue * f32(0.5)), 0, 255)
+    L = np.clip(np.rint(lum * f32(255.0)), 0, 255)
+    S = np.clip(np.rint(sat * f32(255.0)), 0, 255)
+    return np.stack([H, L, S], axis=-1).astype(np.uint8)
+
+
+_HLS_SECTOR = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+
+
+def hls2bgr(hls: np.ndarray) -> np.ndarray:
+    """cvtColor(COLOR_HLS2BGR) on 8UC3: float32, rint at the end; equal to cv2 4.13.0 on all 180*2^16 triples
+    (and for H >= 180, which a stretched H plane can hold: the sector index wraps modulo 6)."""
+    f32 = np.float32
+    h = hls[..., 0].astype(f32)
+    lum = hls[..., 1].astype(f32) * f32(1 / 255.0)
+    s = hls[..., 2].astype(f32) * f32(1 / 255.0)
+    p2 = np.where(lum <= f32(0.5), lum * (f32(1) + s), lum + s - lum * s)
+    p1 = f32(2) * lum - p2
+    hh = h * f32(6 / 180.0)
+    sec = np.floor(hh)
+    fr = hh - sec
+    sec = sec.astype(np.int32) % 6
+    d = p2 - p1
+    tab = np.stack([p2, p1, p1 + d * (f32(1) - fr), p1 + d * fr], 0).reshape(4, -1)
+    idx = np.arange(h.size)
+    secf = sec.reshape(-1)
+    out = np.stack([tab[_HLS_SECTOR[secf, k], idx].reshape(h.shape) for k in range(3)], axis=-1)
+    out = np.where((hls[..., 2] == 0)[..., None], lum[..., None], out)
+    return np.clip(np.rint(out * f32(255.0)), 0, 255).astype(np.uint8)
+
+
 # ----------------------------------------------------------------------------------------
 # histretch CLI channel loop (histretch.cpp:219-254)
 # ----------------------------------------------------------------------------------------
@@ -248,8 +319,9 @@ def histretch_frame(
     order: str = "intended",
     hsv_rounding: str = "cv2",
 ) -> np.ndarray:
-    """Channel loop of the histretch CLI.  Supports the BGR, HSV and YCrCb letters (the HLS / Lab
-    spaces are row N2 of SURVEY 8f).
+    """Channel loop of the histretch CLI.  Supports the BGR, HSV, HLS and YCrCb letters (Lab is row N2 of
+    SURVEY 8f).  Note the letter -> plane map of numChannel: in HLS (plane order H, L, S) the letter 's' is
+    plane 1 = L and 'l' is plane 2 = S, exactly as the reference indexes them.
     order='intended': convert -> stretch -> merge -> convert back (modules/histretch/README.md:4)
     order='literal' : histretch.cpp:232-240 as written - the back-conversion runs on the
                       UNstretched converted image, so the frame becomes its HSV round trip."""
@@ -267,6 +339,11 @@ def histretch_frame(
             else:
                 dst[..., ch] = img_channel_stretch(dst[..., ch], lo, hi)
                 src = hsv2bgr(dst, hsv_rounding)
+        elif sp == 2:  # h, s, l: transformation[1] = BGR2HLS / HLS2BGR
+            dst = bgr2hls(src, "scalar" if hsv_rounding in ("trunc", "rint") else "cv2")
+            if order != "literal":
+                dst[..., ch] = img_channel_stretch(dst[..., ch], lo, hi)
+            src = hls2bgr(dst)
         elif sp == 4:  # Y, C, X: transformation[3] = BGR2YCrCb / YCrCb2BGR (histretch.cpp:155-156)
             dst = bgr2ycrcb(src)
             if order != "literal":

@@ -59,22 +59,36 @@ def test_stretch_edge_cases(ctx, kat):
 def test_histretch_frame(ctx, shape):
     h, w = shape
     for fr in (O.synth_frame(0x5EED0001, 2, w, h), rand_frame(h + w, h, w)):
-        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r", "Y", "C", "X", "YV", "CX"]:
+        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r", "Y", "C", "X", "YV", "CX", "h", "s", "l", "hl", "sV"]:
             got = ctx.histretch(fr, ch, 2, 98)
             assert (got == O.histretch_frame(fr, ch, 2, 98)).all(), (shape, ch)
         got = ctx.histretch(fr, "V", 1, 99, order="literal")
         assert (got == O.histretch_frame(fr, "V", 1, 99, order="literal")).all()
         got = ctx.histretch(fr, "Y", 1, 99, order="literal")
         assert (got == O.histretch_frame(fr, "Y", 1, 99, order="literal")).all()
+        got = ctx.histretch(fr, "s", 1, 99, order="literal")
+        assert (got == O.histretch_frame(fr, "s", 1, 99, order="literal")).all()
+        assert (ctx.histretch(fr, "l", 1, 99, hsv_round="rint") == O.histretch_frame(fr, "l", 1, 99, hsv_rounding="rint")).all()
         for mode in ["trunc", "rint"]:
             assert (ctx.histretch(fr, "V", 1, 99, hsv_round=mode) == O.histretch_frame(fr, "V", 1, 99, hsv_rounding=mode)).all()
+
+
+def test_histretch_hls_all_triples(ctx):
+    """Every BGR triple through BGR2HLS -> HLS2BGR (literal order) and through the 'l' (S plane) stretch, on a width
+    that is all vector body (4096) and one that is all scalar tail (7): the two cv2 code paths of appendix A."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8)
+    for fr in (trip.reshape(4096, 4096, 3), trip[: 7 * 300000].reshape(-1, 7, 3)):
+        assert (ctx.histretch(fr, "h", 2, 98, order="literal") == O.histretch_frame(fr, "h", 2, 98, order="literal")).all()
+        for letter in "hsl":
+            assert (ctx.histretch(fr, letter, 5, 90) == O.histretch_frame(fr, letter, 5, 90)).all(), letter
 
 
 def test_histretch_unsupported_letters(ctx):
     import uwimageproc_b200 as u
 
     fr = rand_frame(1, 16, 16)
-    for ch in ["h", "L", "a"]:
+    for ch in ["L", "a", "b"]:
         with pytest.raises(u.UwipError) as e:
             ctx.histretch(fr, ch)
         assert e.value.status == -3

@@ -82,6 +82,28 @@ def test_histretch_ycrcb_letters(kat):
     assert O.crc32(O.histretch_frame(fr, "X", 2, 98, order="literal")) == kat["histretch_ycrcb"]["literal"]
 
 
+def test_hls_conversions_and_letters(kat):
+    """h, s, l letters (histretch.cpp:155-156, transformation[1]); goldens made with cv2 doing the conversions."""
+    e = kat["hls"]
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8)
+    body = trip.reshape(4096, 4096, 3)
+    tail = trip[: 7 * ((1 << 24) // 7)].reshape(-1, 7, 3)
+    assert O.crc32(O.bgr2hls(body)) == e["all_bgr2hls_body_crc"]
+    assert O.crc32(O.bgr2hls(tail)) == e["all_bgr2hls_tail7_crc"]
+    assert O.crc32(O.hls2bgr(body)) == e["all_hls2bgr_body_crc"]
+    assert O.crc32(O.hls2bgr(tail)) == e["all_hls2bgr_tail7_crc"]
+    bgr = np.random.default_rng(1).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    assert O.crc32(O.bgr2hls(bgr)) == e["K2_hls_crc"]
+    assert O.crc32(O.hls2bgr(O.bgr2hls(bgr))) == e["K2_hls2bgr_crc"]
+    for key, v in e["histretch"].items():
+        W, H = map(int, key.split("x"))
+        fr = O.synth_frame(0x5EED0001, 2, W, H)
+        for letter in "hsl":
+            assert O.crc32(O.histretch_frame(fr, letter, 2, 98)) == v[letter], (key, letter)
+        assert O.crc32(O.histretch_frame(fr, "l", 2, 98, order="literal")) == v["literal"]
+
+
 def test_exhaustive_colour_tables(kat):
     g = np.arange(1 << 24, dtype=np.uint32)
     allbgr = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)

@@ -163,7 +163,10 @@ __host__ __device__ inline double dunkey(unsigned long long k) {
 __device__ __forceinline__ int hsv_sdiv(int i) { return i ? ((255 << 12) * 2 + i) / (2 * i) : 0; }
 __device__ __forceinline__ int hsv_hdiv(int i) { return i ? (2 * 122880 + i) / (2 * i) : 0; }
 
-enum Channel { CH_B = 0, CH_G = 1, CH_R = 2, CH_H = 3, CH_S = 4, CH_V = 5, CH_Y = 6, CH_CR = 7, CH_CB = 8 };
+enum Channel {
+  CH_B = 0, CH_G = 1, CH_R = 2, CH_H = 3, CH_S = 4, CH_V = 5, CH_Y = 6, CH_CR = 7, CH_CB = 8,
+  CH_HLS_H = 9, CH_HLS_L = 10, CH_HLS_S = 11  // planes 0, 1, 2 of BGR2HLS (letters 'h', 's', 'l': numChannel maps 's' -> 1, 'l' -> 2)
+};
 
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
@@ -249,6 +252,62 @@ __device__ __forceinline__ void ycrcb2bgr_u8(int Y, int Cr, int Cb, int& b, int&
   r = min(max(r, 0), 255);
 }
 
+// cvtColor(BGR2HLS) 8-bit (planes H in [0,180), L, S): float32 on k/255.  cv2 4.13.0 runs the first 8*floor(W/8)
+// pixels of a row through a vector body and the rest through the scalar tail; they differ in the S denominator
+// and in whether `h += 360` is fused with the product (oracle bgr2hls, pinned on all 2^24 triples for both).
+__device__ __forceinline__ void bgr2hls_u8(int bi, int gi, int ri, bool body, int& H, int& L, int& S) {
+  const float k255 = 1.0f / 255.0f;
+  float b = __fmul_rn((float)bi, k255), g = __fmul_rn((float)gi, k255), r = __fmul_rn((float)ri, k255);
+  float vmax = fmaxf(fmaxf(b, g), r), vmin = fminf(fminf(b, g), r);
+  float diff = __fsub_rn(vmax, vmin), vs = __fadd_rn(vmax, vmin);
+  float lum = __fmul_rn(vs, 0.5f);
+  float hue = 0.f, sat = 0.f;
+  if (diff > 1.1920928955078125e-07f) {  // FLT_EPSILON
+    float den = body ? __fsub_rn(2.0f, vs) : __fsub_rn(__fsub_rn(2.0f, vmax), vmin);
+    sat = __fdiv_rn(diff, lum < 0.5f ? vs : den);
+    float dinv = __fdiv_rn(60.0f, diff);
+    float d, add;
+    if (vmax == r) { d = __fsub_rn(g, b); add = 0.f; }
+    else if (vmax == g) { d = __fsub_rn(b, r); add = 120.f; }
+    else { d = __fsub_rn(r, g); add = 240.f; }
+    hue = (add == 0.f) ? __fmul_rn(d, dinv) : __fmaf_rn(d, dinv, add);
+    if (hue < 0.f) hue = body ? __fmaf_rn(d, dinv, add + 360.f) : __fadd_rn(hue, 360.f);
+  }
+  H = min(max(__float2int_rn(__fmul_rn(hue, 0.5f)), 0), 255);
+  L = min(max(__float2int_rn(__fmul_rn(lum, 255.0f)), 0), 255);
+  S = min(max(__float2int_rn(__fmul_rn(sat, 255.0f)), 0), 255);
+}
+
+// cvtColor(HLS2BGR) 8-bit: float32, rint at the end (oracle hls2bgr; H >= 180 wraps the sector modulo 6).
+__device__ __forceinline__ void hls2bgr_u8(int H, int L, int S, int& b, int& g, int& r) {
+  const float k255 = 1.0f / 255.0f;
+  float lum = __fmul_rn((float)L, k255);
+  float fb = lum, fg = lum, fr = lum;
+  if (S != 0) {
+    float s = __fmul_rn((float)S, k255);
+    float p2 = (lum <= 0.5f) ? __fmul_rn(lum, __fadd_rn(1.0f, s)) : __fsub_rn(__fadd_rn(lum, s), __fmul_rn(lum, s));
+    float p1 = __fsub_rn(__fmul_rn(2.0f, lum), p2);
+    float hh = __fmul_rn((float)H, 6.0f / 180.0f);
+    float fsec = floorf(hh);
+    float f = __fsub_rn(hh, fsec);
+    int sec = ((int)fsec) % 6;
+    float d = __fsub_rn(p2, p1);
+    float t2 = __fadd_rn(p1, __fmul_rn(d, __fsub_rn(1.0f, f)));
+    float t3 = __fadd_rn(p1, __fmul_rn(d, f));
+    switch (sec) {  // (b,g,r) <- {p2,p1,t2,t3}: {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+      case 0: fb = p1; fg = t3; fr = p2; break;
+      case 1: fb = p1; fg = p2; fr = t2; break;
+      case 2: fb = t3; fg = p2; fr = p1; break;
+      case 3: fb = p2; fg = t2; fr = p1; break;
+      case 4: fb = p2; fg = p1; fr = t3; break;
+      default: fb = t2; fg = p1; fr = p2; break;
+    }
+  }
+  b = min(max(__float2int_rn(__fmul_rn(fb, 255.0f)), 0), 255);
+  g = min(max(__float2int_rn(__fmul_rn(fg, 255.0f)), 0), 255);
+  r = min(max(__float2int_rn(__fmul_rn(fr, 255.0f)), 0), 255);
+}
+
 // saturate_cast<uchar>(cvRound(x)) : NaN / inf -> INT_MIN -> 0
 __device__ __forceinline__ int sat_rint_u8(float x) {
   if (!(fabsf(x) <= 3.0e9f)) return 0;  // NaN, inf (and absurdly large) -> cvRound gives INT_MIN
@@ -275,7 +334,8 @@ struct ChainCfg {
 
 // histretch.cu
 int k_histogram_plane(uwip_ctx* ctx, const uint8_t* d_plane, int n_planes, size_t n_px, uint32_t* d_hist);
-int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n_frames, int w, int h, int channel, uint32_t* d_hist);
+int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n_frames, int w, int h, int channel, uint32_t* d_hist,
+                      int hsv_round = UWIP_HSV_ROUND_CV2_4_13);
 int k_percentile_lut(uwip_ctx* ctx, const uint32_t* d_hist, int n, int w, int h, int lo, int hi, FrameState* fs, uint8_t* d_lut);
 int k_apply_lut_plane(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n_planes, size_t n_px, const uint8_t* d_lut);
 int k_apply_lut_frame(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n_frames, int w, int h, int channel, const uint8_t* d_lut, bool use_lut, int hsv_round);

@@ -35,7 +35,7 @@ __device__ __forceinline__ void px_set(Px16& r, int idx, int v) {
 }
 
 template <int CH>
-__device__ __forceinline__ int extract_channel(int b, int g, int r, const int* sdiv, const int* hdiv) {
+__device__ __forceinline__ int extract_channel(int b, int g, int r, const int* sdiv, const int* hdiv, bool hls_body = false) {
   if (CH == CH_B) return b;
   if (CH == CH_G) return g;
   if (CH == CH_R) return r;
@@ -44,6 +44,11 @@ __device__ __forceinline__ int extract_channel(int b, int g, int r, const int* s
     int Y, Cr, Cb;
     bgr2ycrcb_u8(b, g, r, Y, Cr, Cb);
     return CH == CH_Y ? Y : (CH == CH_CR ? Cr : Cb);
+  }
+  if (CH == CH_HLS_H || CH == CH_HLS_L || CH == CH_HLS_S) {
+    int H, L, S;
+    bgr2hls_u8(b, g, r, hls_body, H, L, S);
+    return CH == CH_HLS_H ? H : (CH == CH_HLS_L ? L : S);
   }
   int h, s, v;
   bgr2hsv_u8(b, g, r, sdiv, hdiv, h, s, v);
@@ -92,7 +97,8 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_plane_kernel(const uint8_t*
 // frames: grid (blocks, n_frames); histogram of one channel (B,G,R,H,S,V) of a bgr8 frame
 template <int CH>
 __global__ void __launch_bounds__(HIST_THREADS) hist_frame_kernel(const uint8_t* __restrict__ src, size_t n_px,
-                                                                  uint32_t* __restrict__ hist) {
+                                                                  uint32_t* __restrict__ hist, int w, int hls_body_w) {
+  constexpr bool HLS = (CH == CH_HLS_H || CH == CH_HLS_L || CH == CH_HLS_S);  // the only channels that depend on x
   __shared__ uint32_t sh[HIST_WARPS][256];
   __shared__ int s_sdiv[256], s_hdiv[256];
   for (int i = threadIdx.x; i < HIST_WARPS * 256; i += HIST_THREADS) (&sh[0][0])[i] = 0;
@@ -107,14 +113,19 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_frame_kernel(const uint8_t*
   size_t n16 = vec ? n_px / 16 : 0;
   for (size_t g = (size_t)blockIdx.x * HIST_THREADS + threadIdx.x; g < n16; g += (size_t)gridDim.x * HIST_THREADS) {
     Px16 q = load_px16(p + g * 48);
+    int x0 = HLS ? (int)((g * 16) % (size_t)w) : 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      int v = extract_channel<CH>(px_byte(q, 3 * k), px_byte(q, 3 * k + 1), px_byte(q, 3 * k + 2), s_sdiv, s_hdiv);
+      int xk = x0 + k;
+      if (HLS && xk >= w) xk -= w;  // a 16-pixel group may straddle a row end
+      int v = extract_channel<CH>(px_byte(q, 3 * k), px_byte(q, 3 * k + 1), px_byte(q, 3 * k + 2), s_sdiv, s_hdiv,
+                                  HLS && xk < hls_body_w);
       atomicAdd(&myh[v], 1u);
     }
   }
   for (size_t i = n16 * 16 + (size_t)blockIdx.x * HIST_THREADS + threadIdx.x; i < n_px; i += (size_t)gridDim.x * HIST_THREADS) {
-    int v = extract_channel<CH>(p[3 * i], p[3 * i + 1], p[3 * i + 2], s_sdiv, s_hdiv);
+    int v = extract_channel<CH>(p[3 * i], p[3 * i + 1], p[3 * i + 2], s_sdiv, s_hdiv,
+                                HLS && (int)(i % (size_t)w) < hls_body_w);
     atomicAdd(&myh[v], 1u);
   }
   hist_flush(sh, hist + (size_t)blockIdx.y * 256);
@@ -136,20 +147,26 @@ int k_histogram_plane(uwip_ctx* ctx, const uint8_t* d_plane, int n_planes, size_
   return UWIP_OK;
 }
 
-int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n, int w, int h, int channel, uint32_t* d_hist) {
+static int hls_body_width(int w, int hsv_round) { return hsv_round == UWIP_HSV_ROUND_CV2_4_13 ? 8 * (w / 8) : 0; }
+
+int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n, int w, int h, int channel, uint32_t* d_hist, int hsv_round) {
+  int hbw = hls_body_width(w, hsv_round);
   UWIP_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (size_t)n * 256 * 4, ctx->stream));
   size_t n_px = (size_t)w * h;
   dim3 grid(hist_grid_x(ctx, n_px, n), n);
   switch (channel) {
-    case CH_B: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_B>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_G: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_G>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_R: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_R>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_H: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_H>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_S: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_S>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_V: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_V>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_Y: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_Y>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_CR: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CR>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
-    case CH_CB: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CB>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist); break;
+    case CH_B: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_B>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_G: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_G>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_R: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_R>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_H: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_H>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_S: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_S>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_V: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_V>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_Y: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_Y>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_CR: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CR>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_CB: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_CB>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_HLS_H: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_H>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_HLS_L: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_L>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_HLS_S: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_S>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
   return UWIP_OK;
@@ -260,7 +277,7 @@ int k_apply_lut_plane(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
 // one pixel of the histretch channel loop: (optionally) convert, LUT one channel, convert back
 template <int CH>
 __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint8_t* s_lut, bool use_lut, bool trunc_mode,
-                                              const int* sdiv, const int* hdiv) {
+                                              const int* sdiv, const int* hdiv, bool hls_body) {
   if (CH == CH_B) { if (use_lut) b = s_lut[b]; return; }
   if (CH == CH_G) { if (use_lut) g = s_lut[g]; return; }
   if (CH == CH_R) { if (use_lut) r = s_lut[r]; return; }
@@ -273,6 +290,17 @@ __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint
       if (CH == CH_CB) Cb = s_lut[Cb];
     }
     ycrcb2bgr_u8(Y, Cr, Cb, b, g, r);
+    return;
+  }
+  if (CH == CH_HLS_H || CH == CH_HLS_L || CH == CH_HLS_S) {  // transformation[1]: BGR2HLS / HLS2BGR
+    int H, L, S;
+    bgr2hls_u8(b, g, r, hls_body, H, L, S);
+    if (use_lut) {
+      if (CH == CH_HLS_H) H = s_lut[H];
+      if (CH == CH_HLS_L) L = s_lut[L];
+      if (CH == CH_HLS_S) S = s_lut[S];
+    }
+    hls2bgr_u8(H, L, S, b, g, r);
     return;
   }
   int h, s, v;
@@ -288,7 +316,7 @@ __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint
 // grid (blocks, n_frames).  body_w: pixels with x < body_w truncate in HSV2BGR, the others round.
 template <int CH>
 __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w,
-                                                              int h, const uint8_t* __restrict__ lut, int use_lut, int body_w) {
+                                                              int h, const uint8_t* __restrict__ lut, int use_lut, int body_w, int hls_body_w) {
   __shared__ uint8_t s_lut[256];
   __shared__ int s_sdiv[256], s_hdiv[256];
   s_lut[threadIdx.x] = use_lut ? lut[(size_t)blockIdx.y * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
@@ -306,7 +334,7 @@ __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __r
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       int b = px_byte(q, 3 * k), g = px_byte(q, 3 * k + 1), r = px_byte(q, 3 * k + 2);
-      stretch_pixel<CH>(b, g, r, s_lut, use_lut, (x0 + k) < body_w, s_sdiv, s_hdiv);
+      stretch_pixel<CH>(b, g, r, s_lut, use_lut, (x0 + k) < body_w, s_sdiv, s_hdiv, (x0 + k) < hls_body_w);
       px_set(q, 3 * k, b);
       px_set(q, 3 * k + 1, g);
       px_set(q, 3 * k + 2, r);
@@ -316,7 +344,7 @@ __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __r
   for (size_t i = n16 * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n_px; i += (size_t)gridDim.x * 256) {
     int b = p[3 * i], g = p[3 * i + 1], r = p[3 * i + 2];
     int x = (int)(i % (size_t)w);
-    stretch_pixel<CH>(b, g, r, s_lut, use_lut, x < body_w, s_sdiv, s_hdiv);
+    stretch_pixel<CH>(b, g, r, s_lut, use_lut, x < body_w, s_sdiv, s_hdiv, x < hls_body_w);
     o[3 * i] = (uint8_t)b;
     o[3 * i + 1] = (uint8_t)g;
     o[3 * i + 2] = (uint8_t)r;
@@ -335,7 +363,8 @@ int k_apply_lut_frame(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   dim3 grid(hist_grid_x(ctx, n_px, n), n);
   int bw = body_width(w, hsv_round);
   int ul = use_lut ? 1 : 0;
-#define AL(CHX) UWIP_LAUNCH(ctx, "apply_lut_frame", apply_lut_frame_kernel<CHX>, grid, 256, 0, d_src, d_dst, w, h, d_lut, ul, bw)
+  int hbw = hls_body_width(w, hsv_round);
+#define AL(CHX) UWIP_LAUNCH(ctx, "apply_lut_frame", apply_lut_frame_kernel<CHX>, grid, 256, 0, d_src, d_dst, w, h, d_lut, ul, bw, hbw)
   switch (channel) {
     case CH_B: AL(CH_B); break;
     case CH_G: AL(CH_G); break;
@@ -346,6 +375,9 @@ int k_apply_lut_frame(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
     case CH_Y: AL(CH_Y); break;
     case CH_CR: AL(CH_CR); break;
     case CH_CB: AL(CH_CB); break;
+    case CH_HLS_H: AL(CH_HLS_H); break;
+    case CH_HLS_L: AL(CH_HLS_L); break;
+    case CH_HLS_S: AL(CH_HLS_S); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
 #undef AL
@@ -444,6 +476,9 @@ static int letter_channel(char c) {
     case 'Y': return CH_Y;
     case 'C': return CH_CR;
     case 'X': return CH_CB;
+    case 'h': return CH_HLS_H;
+    case 's': return CH_HLS_L;  // numChannel('s') == 1 and plane 1 of BGR2HLS is L
+    case 'l': return CH_HLS_S;  // numChannel('l') == 2 == the S plane
   }
   return -1;
 }
@@ -459,14 +494,14 @@ int histretch_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, in
   for (const char* c = channels; *c; ++c) {
     int sp = uwip_num_space(*c);
     if (sp == -1) continue;  // "Option not recognized, skipping..."
-    if (sp == 2 || sp == 3) {  // HLS, Lab
+    if (sp == 3) {  // Lab
       uwip_set_err(ctx, "channel letter '%c' (colour space %d) is not built yet (SURVEY 8f N2)", *c, sp);
       return UWIP_ERR_UNSUPPORTED;
     }
     int ch = letter_channel(*c);
     bool literal_hsv = (sp != 0 && order == UWIP_ORDER_LITERAL);  // literal order: the frame becomes its colour-space round trip
     if (!literal_hsv) {
-      UWIP_CHECK(k_histogram_frame(ctx, cur, n, w, h, ch, d_hist));
+      UWIP_CHECK(k_histogram_frame(ctx, cur, n, w, h, ch, d_hist, hsv_round));
       UWIP_CHECK(k_percentile_lut(ctx, d_hist, n, w, h, lo, hi, nullptr, d_lut));
     }
     UWIP_CHECK(k_apply_lut_frame(ctx, cur, d_dst, n, w, h, ch, d_lut, !literal_hsv, hsv_round));
