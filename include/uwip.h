@@ -199,6 +199,18 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n_frame
 #define UWIP_FRAME_NAN 1
 int uwip_last_frame_flags(uwip_ctx* ctx, int n_frames, int32_t* flags_host);
 
+/* ---- modules/videostrip: calcBlur (the frame-quality gate in front of the chain) */
+/* float calcBlur(Mat frame), videostrip.cpp:170-184 (declared videostrip.hpp:98; calcBlurGPU :39-60 is the
+ * cv::cuda twin): BGR2GRAY -> Laplacian(grey, laplacian, grey.type(), CV_16S) = 8-bit output, aperture 3
+ * (kernel [2 0 2; 0 -8 0; 2 0 2], reflect-101) -> meanStdDev -> (float)stdev.  aperture = 3 is that call;
+ * aperture = 1 is the kernel [0 1 0; 1 -4 1; 0 1 0] that calcBlurGPU requests (videostrip.cpp:48).
+ * mean_std (optional): the doubles meanStdDev returns, {mean, stdev}.  lap (optional): the 8-bit Laplacian. */
+int uwip_calc_blur_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t pitch, int width, int height,
+                        int aperture, float* stdev, double* mean_std, uint8_t* lap, size_t lap_pitch);
+/* batch on device memory: d_mean_std[2f], d_mean_std[2f+1] = mean, stdev of frame f (stream-ordered) */
+int uwip_calc_blur_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, int n_frames, int width, int height,
+                            int aperture, double* d_mean_std);
+
 /* ---- synthetic input + checksums ------------------------------------------------- */
 /* frames first_frame .. first_frame+n_frames-1 of the integer-only generator (twin of
  * oracle/uwip_oracle.py:synth_frame) written to device memory. */

@@ -87,6 +87,26 @@ def hls_goldens(kat):
     kat["hls"] = hls
 
 
+def blur_goldens(kat):
+    """calcBlur (videostrip.cpp:170-184) with cv2 doing cvtColor, Laplacian and meanStdDev."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    out = {"all_bgr2gray_crc": O.crc32(cv2.cvtColor(trip, cv2.COLOR_BGR2GRAY)), "frames": {}}
+    cases = [("synth", 0x5EED0002, 1, 1920, 1080), ("synth", 0x5EED0002, 3, 479, 321), ("rand", 11, 0, 333, 100),
+             ("rand", 12, 0, 1, 1), ("rand", 13, 0, 5, 1), ("rand", 14, 0, 1, 7), ("rand", 15, 0, 31, 2), ("synth", 0x5EED0004, 0, 3840, 2160)]
+    for kind, seed, f, W, H in cases:
+        fr = O.synth_frame(seed, f, W, H) if kind == "synth" else np.random.default_rng(seed).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        grey = cv2.cvtColor(fr, cv2.COLOR_BGR2GRAY)
+        e = {"frame_crc": O.crc32(fr)}
+        for ap in (1, 3):
+            lap = cv2.Laplacian(grey, cv2.CV_8U, ksize=ap)  # aperture 3 is what videostrip.cpp:175 passes as CV_16S
+            m, sd = cv2.meanStdDev(lap)
+            e["ap%d" % ap] = {"lap_crc": O.crc32(lap), "mean": float(m[0, 0]), "stdev": float(sd[0, 0]),
+                              "calcBlur": float(np.float32(sd[0, 0]))}
+        out["frames"]["%s_%x_%d_%dx%d" % (kind, seed, f, W, H)] = e
+    kat["calcblur"] = out
+
+
 def main():
     kat = {"cv2": cv2.__version__, "numpy": np.__version__}
 
@@ -278,6 +298,7 @@ def main():
     kat["histretch_ycrcb"] = ycx
     kat["synth_1080p_f0_crc"] = O.crc32(O.synth_frame(0x5EED0003, 0, 1920, 1080))
     hls_goldens(kat)
+    blur_goldens(kat)
 
     with open(os.path.join(GOLD, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1, sort_keys=True)
@@ -285,11 +306,14 @@ def main():
 
 
 if __name__ == "__main__":
-    if "--only-hls" in sys.argv:  # add the HLS vectors to an existing kat.json without re-running the rest
+    if "--only-hls" in sys.argv or "--only-blur" in sys.argv:  # add vectors to an existing kat.json without re-running the rest
         path = os.path.join(GOLD, "kat.json")
         with open(path) as f:
             kat = json.load(f)
-        hls_goldens(kat)
+        if "--only-hls" in sys.argv:
+            hls_goldens(kat)
+        if "--only-blur" in sys.argv:
+            blur_goldens(kat)
         with open(path, "w") as f:
             json.dump(kat, f, indent=1, sort_keys=True)
     else:

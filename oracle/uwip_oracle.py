@@ -355,6 +355,54 @@ def histretch_frame(
 
 
 # ----------------------------------------------------------------------------------------
+# videostrip calcBlur (videostrip.cpp:170-184) - SURVEY 8f row N4
+# ----------------------------------------------------------------------------------------
+
+
+def bgr2gray(bgr: np.ndarray) -> np.ndarray:
+    """cvtColor(COLOR_BGR2GRAY) on 8UC3 as cv2 4.13.0 computes it: Q15 (9798 R + 19235 G + 3735 B + 2^14) >> 15
+    (equal on all 2^24 triples; OpenCV 3.4.6 documents the Q14 triple 4899/9617/1868, which differs by one level on
+    0.26 % of the triples)."""
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    return ((9798 * r + 19235 * g + 3735 * b + 16384) >> 15).astype(np.uint8)
+
+
+def _reflect101(n: int) -> np.ndarray:
+    idx = np.arange(-1, n + 1)
+    if n == 1:
+        return np.zeros_like(idx)
+    return np.where(idx < 0, -idx, np.where(idx >= n, 2 * n - 2 - idx, idx))
+
+
+def laplacian3_u8(grey: np.ndarray, aperture: int = 3) -> np.ndarray:
+    """Laplacian(grey, dst, CV_8U, ksize=3) - what `Laplacian(grey, laplacian, grey.type(), CV_16S)` at
+    videostrip.cpp:175 asks for (third argument = depth CV_8U, fourth = aperture, CV_16S == 3):
+    kernel [2 0 2; 0 -8 0; 2 0 2], BORDER_REFLECT_101, saturated to 8 bits.  aperture=1: [0 1 0; 1 -4 1; 0 1 0],
+    the kernel calcBlurGPU requests from cv::cuda::createLaplacianFilter (videostrip.cpp:48)."""
+    h, w = grey.shape
+    P = grey.astype(np.int64)[np.ix_(_reflect101(h), _reflect101(w))]
+    if aperture == 3:
+        L = 2 * (P[:-2, :-2] + P[:-2, 2:] + P[2:, :-2] + P[2:, 2:]) - 8 * P[1:-1, 1:-1]
+    else:
+        L = P[:-2, 1:-1] + P[2:, 1:-1] + P[1:-1, :-2] + P[1:-1, 2:] - 4 * P[1:-1, 1:-1]
+    return np.clip(L, 0, 255).astype(np.uint8)
+
+
+def mean_stddev_u8(plane: np.ndarray):
+    """cv::meanStdDev on 8U: integer sums, then scale = 1/N, mean = s*scale, var = max(sq*scale - mean^2, 0)."""
+    p = plane.astype(np.int64)
+    scale = 1.0 / p.size
+    mean = float(int(p.sum())) * scale
+    var = max(float(int((p * p).sum())) * scale - mean * mean, 0.0)
+    return mean, float(np.sqrt(var))
+
+
+def calc_blur(bgr: np.ndarray, aperture: int = 3) -> np.float32:
+    """float calcBlur(Mat frame), videostrip.cpp:170-184: the standard deviation of the Laplacian, returned as float."""
+    return np.float32(mean_stddev_u8(laplacian3_u8(bgr2gray(bgr), aperture))[1])
+
+
+# ----------------------------------------------------------------------------------------
 # CLAHE (cv::CLAHE::apply, 8-bit; SURVEY appendix A.2)
 # ----------------------------------------------------------------------------------------
 

@@ -84,6 +84,42 @@ def test_histretch_hls_all_triples(ctx):
             assert (ctx.histretch(fr, letter, 5, 90) == O.histretch_frame(fr, letter, 5, 90)).all(), letter
 
 
+def test_calcblur(ctx, kat):
+    """calcBlur (videostrip.cpp:170-184): 8-bit Laplacian bit-exact, mean / stdev equal to cv::meanStdDev's doubles."""
+    from tests.test_oracle_golden import _blur_case
+
+    for key, v in kat["calcblur"]["frames"].items():
+        fr = _blur_case(key)
+        for ap in (1, 3):
+            sd, (mean, std), lap = ctx.calc_blur(fr, return_all=True, aperture=ap)
+            e = v["ap%d" % ap]
+            assert O.crc32(lap) == e["lap_crc"], (key, ap)
+            assert (mean, std) == (e["mean"], e["stdev"]), (key, ap)
+            assert float(sd) == e["calcBlur"] == float(O.calc_blur(fr, ap))
+    # pitched input, ragged width (strip of 240 columns + 1) and the batch entry point on device memory
+    big = rand_frame(77, 70, 250)
+    view = big[3:67, 5:246]
+    assert float(ctx.calc_blur(view)) == float(O.calc_blur(np.ascontiguousarray(view)))
+    import uwimageproc_b200 as u
+
+    with pytest.raises(u.UwipError):
+        ctx.calc_blur(view, aperture=5)
+
+
+def test_calcblur_batch_4k(ctx):
+    torch = pytest.importorskip("torch")
+    n, W, H = 6, 3840, 2160
+    d = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    out = torch.empty((n, 2), dtype=torch.float64, device="cuda")
+    ctx.synth_dev(d.data_ptr(), 0x5EED0004, 0, n, W, H)
+    ctx.calc_blur_dev(d.data_ptr(), n, W, H, out.data_ptr())
+    ctx.synchronize()
+    got = out.cpu().numpy()
+    for f in (0, n - 1):
+        fr = d[f].cpu().numpy()
+        assert tuple(got[f]) == O.mean_stddev_u8(O.laplacian3_u8(O.bgr2gray(fr)))
+
+
 def test_histretch_unsupported_letters(ctx):
     import uwimageproc_b200 as u
 

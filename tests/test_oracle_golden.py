@@ -104,6 +104,30 @@ def test_hls_conversions_and_letters(kat):
         assert O.crc32(O.histretch_frame(fr, "l", 2, 98, order="literal")) == v["literal"]
 
 
+def _blur_case(key):
+    kind, seed, f, size = key.split("_")
+    W, H = map(int, size.split("x"))
+    if kind == "synth":
+        return O.synth_frame(int(seed, 16), int(f), W, H)
+    return np.random.default_rng(int(seed, 16)).integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+
+def test_calcblur_goldens(kat):
+    """calcBlur (videostrip.cpp:170-184): goldens made by cv2 (cvtColor, Laplacian, meanStdDev); exact, doubles included."""
+    e = kat["calcblur"]
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert O.crc32(O.bgr2gray(trip)) == e["all_bgr2gray_crc"]
+    for key, v in e["frames"].items():
+        fr = _blur_case(key)
+        assert O.crc32(fr) == v["frame_crc"]
+        for ap in (1, 3):
+            lap = O.laplacian3_u8(O.bgr2gray(fr), ap)
+            assert O.crc32(lap) == v["ap%d" % ap]["lap_crc"], (key, ap)
+            assert O.mean_stddev_u8(lap) == (v["ap%d" % ap]["mean"], v["ap%d" % ap]["stdev"]), (key, ap)
+            assert float(O.calc_blur(fr, ap)) == v["ap%d" % ap]["calcBlur"]
+
+
 def test_exhaustive_colour_tables(kat):
     g = np.arange(1 << 24, dtype=np.uint32)
     allbgr = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)

@@ -236,6 +236,20 @@ class Context:
         p = params or self.dehaze_params()
         self._ck(self.lib.uwip_bgdehaze_bgr8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, C.byref(p)))
 
+    # ---- videostrip calcBlur (videostrip.cpp:170-184) ------------------------------------------------
+    def calc_blur(self, frame, return_all=False, aperture=3):
+        """float32 stdev of the 8-bit aperture-3 Laplacian of the grey frame; return_all: (stdev, (mean, stdev) f64, laplacian u8)."""
+        f = _frame(frame)
+        sd = C.c_float()
+        ms = (C.c_double * 2)()
+        lap = np.empty(f.shape[:2], np.uint8) if return_all else None
+        self._ck(self.lib.uwip_calc_blur_bgr8(self.h, _ptr(f), f.strides[0], f.shape[1], f.shape[0], int(aperture), C.byref(sd), ms,
+                                              _ptr(lap) if return_all else None, lap.strides[0] if return_all else 0))
+        return (np.float32(sd.value), (ms[0], ms[1]), lap) if return_all else np.float32(sd.value)
+
+    def calc_blur_dev(self, d_src, n, width, height, d_mean_std, aperture=3):
+        self._ck(self.lib.uwip_calc_blur_bgr8_dev(self.h, _ptr(d_src), n, width, height, int(aperture), _ptr(d_mean_std)))
+
     def synth_dev(self, d_dst, seed, first_frame, n, width, height):
         self._ck(self.lib.uwip_synth_bgr8_dev(self.h, _ptr(d_dst), seed & 0xFFFFFFFF, first_frame, n, width, height))
 

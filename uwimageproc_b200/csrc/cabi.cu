@@ -378,6 +378,32 @@ int uwip_aclahe_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t sp, uint8_t* dst,
   return stage_out(ctx, d, dst, dp, w, h, 3);
 }
 
+// ---- videostrip calcBlur ------------------------------------------------------------------------------
+int uwip_calc_blur_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, int n, int w, int h, int aperture, double* d_mean_std) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, d_src && d_mean_std && n >= 1 && w >= 1 && h >= 1 && (aperture == 1 || aperture == 3), "bad argument");
+  return calc_blur_frames_dev(ctx, d_src, n, w, h, aperture, d_mean_std, nullptr);
+}
+int uwip_calc_blur_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t pitch, int w, int h, int aperture, float* stdev, double* mean_std,
+                        uint8_t* lap, size_t lap_pitch) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, stdev || mean_std || lap, "no output requested");
+  UWIP_REQUIRE(ctx, aperture == 1 || aperture == 3, "aperture must be 1 or 3");
+  uint8_t* d;
+  UWIP_CHECK(stage_in(ctx, SLOT_STAGE_IN, src, pitch, w, h, 3, &d));
+  double* d_out = (double*)uwip_slot(ctx, SLOT_BLUROUT, 16);
+  uint8_t* d_lap = lap ? (uint8_t*)uwip_slot(ctx, SLOT_STAGE_OUT, (size_t)w * h) : nullptr;
+  if (!d_out || (lap && !d_lap)) return UWIP_ERR_NOMEM;
+  UWIP_CHECK(calc_blur_frames_dev(ctx, d, 1, w, h, aperture, d_out, d_lap));
+  double ms[2];
+  UWIP_CUDA(ctx, cudaMemcpyAsync(ms, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lap) UWIP_CHECK(stage_out(ctx, d_lap, lap, lap_pitch, w, h, 1));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stdev) *stdev = (float)ms[1];  // `return stdev.val[0];` from a float function
+  if (mean_std) { mean_std[0] = ms[0]; mean_std[1] = ms[1]; }
+  return UWIP_OK;
+}
+
 // ---- bgdehaze -----------------------------------------------------------------------------------------
 void uwip_dehaze_defaults(uwip_dehaze_params* p) {
   if (!p) return;

@@ -64,6 +64,8 @@ enum Slot {
   SLOT_YCC,           // dehaze: packed Yi Cri Cbi Yj (u32)
   SLOT_STAB,          // dehaze: exposure-ratio table (f64 x 65536 per frame)
   SLOT_SPLANE,        // dehaze: exposure ratio per pixel (f32)
+  SLOT_BLURSUMS,      // calcBlur: per-frame sum and sum of squares of the 8-bit Laplacian (u64 x2)
+  SLOT_BLUROUT,       // calcBlur: per-frame mean, stdev (f64 x2)
 };
 
 const char* uwip_set_err(uwip_ctx* ctx, const char* fmt, ...);
@@ -334,6 +336,7 @@ struct ChainCfg {
 
 // histretch.cu
 int k_histogram_plane(uwip_ctx* ctx, const uint8_t* d_plane, int n_planes, size_t n_px, uint32_t* d_hist);
+int calc_blur_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, int n, int w, int h, int aperture, double* d_mean_std, uint8_t* d_lap);
 int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n_frames, int w, int h, int channel, uint32_t* d_hist,
                       int hsv_round = UWIP_HSV_ROUND_CV2_4_13);
 int k_percentile_lut(uwip_ctx* ctx, const uint32_t* d_hist, int n, int w, int h, int lo, int hi, FrameState* fs, uint8_t* d_lut);
