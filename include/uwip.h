@@ -37,7 +37,7 @@ typedef enum uwip_status {
   UWIP_OK = 0,
   UWIP_ERR_INVALID = -1,     /* bad pointer / size / parameter (reference: UB or silent skip)   */
   UWIP_ERR_CUDA = -2,        /* CUDA runtime error, text in uwip_last_error                     */
-  UWIP_ERR_UNSUPPORTED = -3, /* valid in the reference but not built yet (Lab letters)           */
+  UWIP_ERR_UNSUPPORTED = -3, /* reserved: valid in the reference but not built (no such case now) */
   UWIP_ERR_NOMEM = -4
 } uwip_status;
 
@@ -103,8 +103,8 @@ int uwip_channel_stretch_u8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_
                                 int height, int lo, int hi);
 
 /* ---- modules/histretch/src/histretch.cpp:219-254 (the -c=<letters> channel loop) ------------ */
-/* channels: ordered letters; RGB, HSV, HLS ('hsl') and YCrCb ('YCX') letters are built (Lab 'Lab'
- * returns UWIP_ERR_UNSUPPORTED: SURVEY 8f row N2); unknown letters are skipped like the CLI does.
+/* channels: ordered letters; every letter of the CLI is built - RGB, HSV, HLS ('hsl'), Lab ('Lab') and
+ * YCrCb ('YCX'), each equal to cv2 4.13.0 on all 2^24 triples; unknown letters are skipped like the CLI does.
  * The CLI hard-codes lo=2, hi=98 (histretch.cpp:154). */
 int uwip_histretch_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t src_pitch, uint8_t* dst,
                         size_t dst_pitch, int width, int height, const char* channels, int lo,

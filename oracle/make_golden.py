@@ -107,6 +107,29 @@ def blur_goldens(kat):
     kat["calcblur"] = out
 
 
+def lab_goldens(kat):
+    """Lab letters L, a, b of histretch (transformation[2], histretch.cpp:155-156): cv2 does every conversion."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    lab = {
+        "all_bgr2lab_crc": O.crc32(cv2.cvtColor(trip, cv2.COLOR_BGR2Lab)),
+        "all_lab2bgr_crc": O.crc32(cv2.cvtColor(trip, cv2.COLOR_Lab2BGR)),  # the same triples read as (L, a, b)
+        "tail7_bgr2lab_crc": O.crc32(cv2.cvtColor(trip.reshape(-1, 3)[: 7 * 100000].reshape(-1, 7, 3), cv2.COLOR_BGR2Lab)),
+    }
+    letters = {}
+    for (W, H) in ((479, 321), (640, 360)):
+        fr = O.synth_frame(0x5EED0001, 2, W, H)
+        e = {}
+        for letter, ch in (("L", 0), ("a", 1), ("b", 2)):
+            d = cv2.cvtColor(fr, cv2.COLOR_BGR2Lab)
+            d[..., ch] = O.img_channel_stretch(np.ascontiguousarray(d[..., ch]), 2, 98)
+            e[letter] = O.crc32(cv2.cvtColor(d, cv2.COLOR_Lab2BGR))
+        e["literal"] = O.crc32(cv2.cvtColor(cv2.cvtColor(fr, cv2.COLOR_BGR2Lab), cv2.COLOR_Lab2BGR))
+        letters["%dx%d" % (W, H)] = e
+    lab["histretch"] = letters
+    kat["lab"] = lab
+
+
 def main():
     kat = {"cv2": cv2.__version__, "numpy": np.__version__}
 
@@ -299,6 +322,7 @@ def main():
     kat["synth_1080p_f0_crc"] = O.crc32(O.synth_frame(0x5EED0003, 0, 1920, 1080))
     hls_goldens(kat)
     blur_goldens(kat)
+    lab_goldens(kat)
 
     with open(os.path.join(GOLD, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1, sort_keys=True)
@@ -306,7 +330,7 @@ def main():
 
 
 if __name__ == "__main__":
-    if "--only-hls" in sys.argv or "--only-blur" in sys.argv:  # add vectors to an existing kat.json without re-running the rest
+    if any(a.startswith("--only-") for a in sys.argv):  # add vectors to an existing kat.json without re-running the rest
         path = os.path.join(GOLD, "kat.json")
         with open(path) as f:
             kat = json.load(f)
@@ -314,6 +338,8 @@ if __name__ == "__main__":
             hls_goldens(kat)
         if "--only-blur" in sys.argv:
             blur_goldens(kat)
+        if "--only-lab" in sys.argv:
+            lab_goldens(kat)
         with open(path, "w") as f:
             json.dump(kat, f, indent=1, sort_keys=True)
     else:

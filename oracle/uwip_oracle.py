@@ -306,6 +306,105 @@ def hls2bgr(hls: np.ndarray) -> np.ndarray:
     return np.clip(np.rint(out * f32(255.0)), 0, 255).astype(np.uint8)
 
 
+
+# ---- 8-bit CIE Lab (cvtColor BGR2Lab / Lab2BGR, D65, sRGB gamma): OpenCV 4's bit-exact integer path ----
+# Restated from the published algorithm (imgproc color_lab.cpp: RGB2Lab_b / Lab2RGBinteger) and pinned against cv2
+# 4.13.0 on all 2^24 triples in both directions (tests/golden/kat.json: lab).  Position independent (no body/tail split).
+_LAB_SHIFT, _GAMMA_SHIFT, _LAB_SHIFT2, _LAB_BASE, _INV_GAMMA_SIZE, _LAB_MIN_AB = 12, 3, 15, 1 << 14, 1 << 12, -8145
+_LAB_WHITE = (0.950456, 1.0, 1.088754)
+_SRGB2XYZ = (0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227)
+_XYZ2SRGB = (3.240479, -1.53715, -0.498535, -0.969256, 1.875991, 0.041556, 0.055648, -0.204043, 1.057311)
+
+
+def lab_tables():
+    """The lookup tables of the 8-bit Lab conversions: (gamma[256], cbrt[3072], fwd coeffs[9], LabToYF[512], invgamma[4096],
+    inv coeffs[9]).  Table values are rint() of float32 products like the source computes them.  The cube-root table is
+    rint(2^15 cbrt(x)) with cbrt in double from the float32 abscissa, except entry 49 (true value 9454.5004, the source's
+    soft-float cbrt lands below the tie: 9454) - fixed by the exhaustive comparison; 8-bit inputs reach entries 0..2040 only."""
+    f32 = np.float32
+    i = np.arange(256)
+    x = i.astype(f32) / f32(255)
+    xd = x.astype(np.float64)
+    g = np.where(xd <= 0.04045, xd / 12.92, ((xd + 0.055) / 1.055) ** 2.4).astype(f32)
+    gamma = np.rint(f32(255 * (1 << _GAMMA_SHIFT)) * g).astype(np.int64)
+    n = 256 * 3 // 2 * (1 << _GAMMA_SHIFT)
+    xi = (f32(1) / (f32(255) * f32(1 << _GAMMA_SHIFT))) * np.arange(n).astype(f32)
+    xd = xi.astype(np.float64)
+    lin = (xd * np.float64(f32(841 / 108.0)) + np.float64(f32(16 / 116.0))).astype(f32).astype(np.float64)
+    cb = np.where(xi < f32(216 / 24389.0), lin, np.cbrt(xd))
+    cbrt = np.rint((1 << _LAB_SHIFT2) * cb).astype(np.int64)
+    cbrt[49] = 9454
+    fwd = np.array([int(np.rint((1 << _LAB_SHIFT) * _SRGB2XYZ[k * 3 + j] / _LAB_WHITE[k])) for k in range(3) for j in range(3)], np.int64)
+    ytab = np.zeros(512, np.int64)
+    B = _LAB_BASE
+    for L in range(256):
+        if L <= 20:
+            y = np.rint(f32(L * B * 20 * 9) / f32(17 * 29 * 29 * 29))
+            ify = np.rint(f32(B) * (f32(16) / f32(116) + f32(L * 5) / f32(3 * 17 * 29)))
+        else:
+            fy = f32(L * 100 * B) / f32(255 * 116) + f32(16 * B) / f32(116)
+            ify = np.rint(fy)
+            y = np.rint(fy * fy * fy / f32(B * B))
+        ytab[2 * L], ytab[2 * L + 1] = int(y), int(ify)
+    xg = (f32(1) / f32(_INV_GAMMA_SIZE)) * np.arange(_INV_GAMMA_SIZE).astype(f32)
+    xd = xg.astype(np.float64)
+    ig = np.where(xd <= 0.0031308, xd * 12.92, np.power(xd, 1 / 2.4) * 1.055 - 0.055).astype(f32)
+    invgamma = np.rint(f32(255) * ig).astype(np.int64)
+    inv = np.array([int(np.rint((1 << _LAB_SHIFT) * _XYZ2SRGB[r * 3 + k] * _LAB_WHITE[k])) for r in range(3) for k in range(3)], np.int64)
+    return gamma, cbrt, fwd, ytab, invgamma, inv
+
+
+_LAB_T = None
+
+
+def _lab_t():
+    global _LAB_T
+    if _LAB_T is None:
+        _LAB_T = lab_tables()
+    return _LAB_T
+
+
+def _descale(v, s):
+    return (v + (1 << (s - 1))) >> s
+
+
+def lab_ab_to_xz(i):
+    """abToXZ_b as a function (the source tabulates it over [-8145, 28719)): C integer division truncates toward zero."""
+    i = np.asarray(i, np.int64)
+    t = i * 108
+    lo = np.where(t >= 0, t // 841, -((-t) // 841)) - (_LAB_BASE * 16 // 116 * 108 // 841)
+    hi = (i * i // _LAB_BASE) * i // _LAB_BASE
+    return np.where(i <= 3390, lo, hi)
+
+
+def bgr2lab(bgr: np.ndarray) -> np.ndarray:
+    """cvtColor(COLOR_BGR2Lab) on 8UC3 (planes L*255/100, a+128, b+128)."""
+    gamma, cbrt, C, _, _, _ = _lab_t()
+    B, G, R = gamma[bgr[..., 0]], gamma[bgr[..., 1]], gamma[bgr[..., 2]]
+    fX = cbrt[_descale(R * C[0] + G * C[1] + B * C[2], _LAB_SHIFT)]
+    fY = cbrt[_descale(R * C[3] + G * C[4] + B * C[5], _LAB_SHIFT)]
+    fZ = cbrt[_descale(R * C[6] + G * C[7] + B * C[8], _LAB_SHIFT)]
+    Lscale = (116 * 255 + 50) // 100
+    Lshift = -((16 * 255 * (1 << _LAB_SHIFT2) + 50) // 100)
+    L = _descale(Lscale * fY + Lshift, _LAB_SHIFT2)
+    a = _descale(500 * (fX - fY) + 128 * (1 << _LAB_SHIFT2), _LAB_SHIFT2)
+    b = _descale(200 * (fY - fZ) + 128 * (1 << _LAB_SHIFT2), _LAB_SHIFT2)
+    return np.clip(np.stack([L, a, b], axis=-1), 0, 255).astype(np.uint8)
+
+
+def lab2bgr(lab: np.ndarray) -> np.ndarray:
+    """cvtColor(COLOR_Lab2BGR) on 8UC3."""
+    _, _, _, ytab, invgamma, C = _lab_t()
+    LL, aa, bb = (lab[..., k].astype(np.int64) for k in range(3))
+    y, ify = ytab[2 * LL], ytab[2 * LL + 1]
+    adiv = ((5 * aa * 53687 + (1 << 7)) >> 13) - 128 * _LAB_BASE // 500
+    bdiv = ((bb * 41943 + (1 << 4)) >> 9) - 128 * _LAB_BASE // 200 + 1
+    x, z = lab_ab_to_xz(ify + adiv), lab_ab_to_xz(ify - bdiv)
+    shift = _LAB_SHIFT + (14 - 12)
+    ch = [invgamma[np.clip(_descale(C[3 * r] * x + C[3 * r + 1] * y + C[3 * r + 2] * z, shift), 0, _INV_GAMMA_SIZE - 1)] for r in range(3)]
+    return np.stack([ch[2], ch[1], ch[0]], axis=-1).astype(np.uint8)
+
+
 # ----------------------------------------------------------------------------------------
 # histretch CLI channel loop (histretch.cpp:219-254)
 # ----------------------------------------------------------------------------------------
@@ -319,8 +418,7 @@ def histretch_frame(
     order: str = "intended",
     hsv_rounding: str = "cv2",
 ) -> np.ndarray:
-    """Channel loop of the histretch CLI.  Supports the BGR, HSV, HLS and YCrCb letters (Lab is row N2 of
-    SURVEY 8f).  Note the letter -> plane map of numChannel: in HLS (plane order H, L, S) the letter 's' is
+    """Channel loop of the histretch CLI.  Supports every letter of the CLI (BGR, HSV, HLS, Lab, YCrCb).  Note the letter -> plane map of numChannel: in HLS (plane order H, L, S) the letter 's' is
     plane 1 = L and 'l' is plane 2 = S, exactly as the reference indexes them.
     order='intended': convert -> stretch -> merge -> convert back (modules/histretch/README.md:4)
     order='literal' : histretch.cpp:232-240 as written - the back-conversion runs on the
@@ -344,13 +442,16 @@ def histretch_frame(
             if order != "literal":
                 dst[..., ch] = img_channel_stretch(dst[..., ch], lo, hi)
             src = hls2bgr(dst)
+        elif sp == 3:  # L, a, b: transformation[2] = BGR2Lab / Lab2BGR
+            dst = bgr2lab(src)
+            if order != "literal":
+                dst[..., ch] = img_channel_stretch(dst[..., ch], lo, hi)
+            src = lab2bgr(dst)
         elif sp == 4:  # Y, C, X: transformation[3] = BGR2YCrCb / YCrCb2BGR (histretch.cpp:155-156)
             dst = bgr2ycrcb(src)
             if order != "literal":
                 dst[..., ch] = img_channel_stretch(dst[..., ch], lo, hi)
             src = ycrcb2bgr(dst)
-        else:
-            raise NotImplementedError("colour space %d (letter %r) is SURVEY 8f row N2" % (sp, c))
     return src
 
 
@@ -395,6 +496,15 @@ def mean_stddev_u8(plane: np.ndarray):
     mean = float(int(p.sum())) * scale
     var = max(float(int((p * p).sum())) * scale - mean * mean, 0.0)
     return mean, float(np.sqrt(var))
+
+
+def golden_frame(key: str) -> np.ndarray:
+    """Input frame of a golden-vector case named `<synth|rand>_<seed hex>_<frame>_<W>x<H>` (tests/golden/kat.json)."""
+    kind, seed, f, size = key.split("_")
+    W, H = map(int, size.split("x"))
+    if kind == "synth":
+        return synth_frame(int(seed, 16), int(f), W, H)
+    return np.random.default_rng(int(seed, 16)).integers(0, 256, (H, W, 3), dtype=np.uint8)
 
 
 def calc_blur(bgr: np.ndarray, aperture: int = 3) -> np.float32:

@@ -59,7 +59,7 @@ def test_stretch_edge_cases(ctx, kat):
 def test_histretch_frame(ctx, shape):
     h, w = shape
     for fr in (O.synth_frame(0x5EED0001, 2, w, h), rand_frame(h + w, h, w)):
-        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r", "Y", "C", "X", "YV", "CX", "h", "s", "l", "hl", "sV"]:
+        for ch in ["V", "S", "H", "R", "G", "B", "HV", "VS", "xV", "r", "Y", "C", "X", "YV", "CX", "h", "s", "l", "hl", "sV", "L", "a", "b", "La", "bV"]:
             got = ctx.histretch(fr, ch, 2, 98)
             assert (got == O.histretch_frame(fr, ch, 2, 98)).all(), (shape, ch)
         got = ctx.histretch(fr, "V", 1, 99, order="literal")
@@ -86,10 +86,8 @@ def test_histretch_hls_all_triples(ctx):
 
 def test_calcblur(ctx, kat):
     """calcBlur (videostrip.cpp:170-184): 8-bit Laplacian bit-exact, mean / stdev equal to cv::meanStdDev's doubles."""
-    from tests.test_oracle_golden import _blur_case
-
     for key, v in kat["calcblur"]["frames"].items():
-        fr = _blur_case(key)
+        fr = O.golden_frame(key)
         for ap in (1, 3):
             sd, (mean, std), lap = ctx.calc_blur(fr, return_all=True, aperture=ap)
             e = v["ap%d" % ap]
@@ -120,14 +118,22 @@ def test_calcblur_batch_4k(ctx):
         assert tuple(got[f]) == O.mean_stddev_u8(O.laplacian3_u8(O.bgr2gray(fr)))
 
 
-def test_histretch_unsupported_letters(ctx):
-    import uwimageproc_b200 as u
+def test_histretch_lab_all_triples(ctx):
+    """Every BGR triple through BGR2Lab -> Lab2BGR (literal order) and through the L, a, b stretches."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8)
+    for fr in (trip.reshape(4096, 4096, 3), trip[: 7 * 300000].reshape(-1, 7, 3)):
+        assert (ctx.histretch(fr, "L", 2, 98, order="literal") == O.histretch_frame(fr, "L", 2, 98, order="literal")).all()
+        for letter in "Lab":
+            assert (ctx.histretch(fr, letter, 5, 90) == O.histretch_frame(fr, letter, 5, 90)).all(), letter
 
-    fr = rand_frame(1, 16, 16)
-    for ch in ["L", "a", "b"]:
-        with pytest.raises(u.UwipError) as e:
-            ctx.histretch(fr, ch)
-        assert e.value.status == -3
+
+def test_histretch_every_letter_of_the_cli(ctx):
+    """-c=RGBHSVhslLabYCX (histretch.cpp:68-74): all fifteen letters in one call, plus unknown ones that are skipped."""
+    fr = O.synth_frame(0x5EED0001, 5, 641, 479)
+    letters = "RGBHSVhslLabYCX"
+    assert (ctx.histretch(fr, letters, 2, 98) == O.histretch_frame(fr, letters, 2, 98)).all()
+    assert (ctx.histretch(fr, "r?Lz", 2, 98) == O.histretch_frame(fr, "L", 2, 98)).all()
 
 
 # ---- aclahe --------------------------------------------------------------------------------------

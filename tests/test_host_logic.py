@@ -124,3 +124,24 @@ def test_two_rank_sharding_gloo(tmp_path):
     for r, p in enumerate(procs):
         assert p.returncode == 0, outs[r]
     assert "rank 0 ok 4 frames" in outs[0] and "rank 1 ok 3 frames" in outs[1]
+
+
+def test_lab_tables_match_the_oracle():
+    """The committed lab_tables.inc (product side, built by csrc/gen_lab_tables.py) holds the oracle's tables."""
+    import re
+
+    from oracle import uwip_oracle as O
+
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uwimageproc_b200", "csrc", "lab_tables.inc")).read()
+
+    def arr(name):
+        m = re.search(name + r"\[\d+\] = \{(.*?)\};", txt, re.S)
+        return np.array([int(v) for v in m.group(1).replace("\n", " ").split(",")], np.int64)
+
+    gamma, cbrt, fwd, yf, invgamma, inv = O.lab_tables()
+    assert (arr("kLabGamma") == gamma).all()
+    assert (arr("kLabCbrt") == cbrt[:2048]).all()
+    assert (arr("kLabYF") == yf).all()
+    assert (arr("kLabInvGamma") == invgamma).all()
+    assert [int(v) for v in re.search(r"LAB_FWD_COEFFS \{(.*?)\}", txt).group(1).split(",")] == list(fwd)
+    assert [int(v) for v in re.search(r"LAB_INV_COEFFS \{(.*?)\}", txt).group(1).split(",")] == list(inv)

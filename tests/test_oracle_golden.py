@@ -104,12 +104,20 @@ def test_hls_conversions_and_letters(kat):
         assert O.crc32(O.histretch_frame(fr, "l", 2, 98, order="literal")) == v["literal"]
 
 
-def _blur_case(key):
-    kind, seed, f, size = key.split("_")
-    W, H = map(int, size.split("x"))
-    if kind == "synth":
-        return O.synth_frame(int(seed, 16), int(f), W, H)
-    return np.random.default_rng(int(seed, 16)).integers(0, 256, (H, W, 3), dtype=np.uint8)
+def test_lab_conversions_and_letters(kat):
+    """L, a, b letters (histretch.cpp:155-156, transformation[2]); goldens made with cv2 doing the conversions."""
+    e = kat["lab"]
+    g = np.arange(1 << 24, dtype=np.uint32)
+    trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert O.crc32(O.bgr2lab(trip)) == e["all_bgr2lab_crc"]
+    assert O.crc32(O.lab2bgr(trip)) == e["all_lab2bgr_crc"]
+    assert O.crc32(O.bgr2lab(trip.reshape(-1, 3)[: 7 * 100000].reshape(-1, 7, 3))) == e["tail7_bgr2lab_crc"]
+    for key, v in e["histretch"].items():
+        W, H = map(int, key.split("x"))
+        fr = O.synth_frame(0x5EED0001, 2, W, H)
+        for letter in "Lab":
+            assert O.crc32(O.histretch_frame(fr, letter, 2, 98)) == v[letter], (key, letter)
+        assert O.crc32(O.histretch_frame(fr, "a", 2, 98, order="literal")) == v["literal"]
 
 
 def test_calcblur_goldens(kat):
@@ -119,7 +127,7 @@ def test_calcblur_goldens(kat):
     trip = np.stack([(g & 255), (g >> 8) & 255, (g >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
     assert O.crc32(O.bgr2gray(trip)) == e["all_bgr2gray_crc"]
     for key, v in e["frames"].items():
-        fr = _blur_case(key)
+        fr = O.golden_frame(key)
         assert O.crc32(fr) == v["frame_crc"]
         for ap in (1, 3):
             lap = O.laplacian3_u8(O.bgr2gray(fr), ap)

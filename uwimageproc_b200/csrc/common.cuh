@@ -167,7 +167,8 @@ __device__ __forceinline__ int hsv_hdiv(int i) { return i ? (2 * 122880 + i) / (
 
 enum Channel {
   CH_B = 0, CH_G = 1, CH_R = 2, CH_H = 3, CH_S = 4, CH_V = 5, CH_Y = 6, CH_CR = 7, CH_CB = 8,
-  CH_HLS_H = 9, CH_HLS_L = 10, CH_HLS_S = 11  // planes 0, 1, 2 of BGR2HLS (letters 'h', 's', 'l': numChannel maps 's' -> 1, 'l' -> 2)
+  CH_HLS_H = 9, CH_HLS_L = 10, CH_HLS_S = 11,  // planes 0, 1, 2 of BGR2HLS (letters 'h', 's', 'l': numChannel maps 's' -> 1, 'l' -> 2)
+  CH_LAB_L = 12, CH_LAB_A = 13, CH_LAB_B = 14   // planes 0, 1, 2 of BGR2Lab (letters 'L', 'a', 'b')
 };
 
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }

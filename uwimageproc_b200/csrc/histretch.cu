@@ -6,6 +6,58 @@
 // HBM-bound byte work: 16-byte vector loads (16 pixels = 3 x uint4), per-warp privatised shared
 // histograms, block prefix scan for the percentile search, LUT apply fused with the colour round trip.
 #include "common.cuh"
+#include "lab_tables.inc"
+
+// ---- 8-bit CIE Lab (cvtColor BGR2Lab / Lab2BGR; histretch letters L, a, b = transformation[2], histretch.cpp:155-156) ----
+// OpenCV 4's bit-exact integer path (RGB2Lab_b / Lab2RGBinteger, D65, sRGB gamma): gamma table -> Q12 matrix ->
+// cube-root table -> L, a, b; back through the L -> (y, f(y)) table, the cubic, the Q12 matrix and the inverse
+// gamma table.  Equal to cv2 4.13.0 on all 2^24 triples in both directions (oracle bgr2lab / lab2bgr).
+template <bool LAB>
+struct LabSmem {};
+template <>
+struct LabSmem<true> {
+  uint16_t gamma[256], cbrt[2048], yf[512];
+  uint8_t invgamma[4096];
+  __device__ void fill(bool fwd, bool inv) {
+    if (fwd) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) gamma[i] = kLabGamma[i];
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) cbrt[i] = kLabCbrt[i];
+    }
+    if (inv) {
+      for (int i = threadIdx.x; i < 512; i += blockDim.x) yf[i] = kLabYF[i];
+      for (int i = threadIdx.x; i < 4096; i += blockDim.x) invgamma[i] = kLabInvGamma[i];
+    }
+  }
+};
+__device__ __forceinline__ void bgr2lab_u8(int b, int g, int r, const LabSmem<true>& t, int& L, int& A, int& Bc) {
+  constexpr int C[9] = LAB_FWD_COEFFS;
+  const int R = t.gamma[r], G = t.gamma[g], B = t.gamma[b];
+  const int fX = t.cbrt[(R * C[0] + G * C[1] + B * C[2] + 2048) >> 12];
+  const int fY = t.cbrt[(R * C[3] + G * C[4] + B * C[5] + 2048) >> 12];
+  const int fZ = t.cbrt[(R * C[6] + G * C[7] + B * C[8] + 2048) >> 12];
+  constexpr int Lscale = (116 * 255 + 50) / 100, Lshift = -((16 * 255 * (1 << 15) + 50) / 100);
+  L = min(max((Lscale * fY + Lshift + 16384) >> 15, 0), 255);
+  A = min(max((500 * (fX - fY) + 128 * 32768 + 16384) >> 15, 0), 255);
+  Bc = min(max((200 * (fY - fZ) + 128 * 32768 + 16384) >> 15, 0), 255);
+}
+__device__ __forceinline__ int lab_ab_to_xz(int i) {  // abToXZ_b as a function; integer division truncates toward zero
+  constexpr int BASE = 1 << 14;
+  return (i <= 3390) ? (i * 108) / 841 - BASE * 16 / 116 * 108 / 841 : (i * i / BASE) * i / BASE;
+}
+__device__ __forceinline__ void lab2bgr_u8(int L, int A, int Bc, const LabSmem<true>& t, int& b, int& g, int& r) {
+  constexpr int C[9] = LAB_INV_COEFFS;
+  constexpr int BASE = 1 << 14;
+  const int y = t.yf[2 * L], ify = t.yf[2 * L + 1];
+  const int adiv = ((5 * A * 53687 + (1 << 7)) >> 13) - 128 * BASE / 500;
+  const int bdiv = ((Bc * 41943 + (1 << 4)) >> 9) - 128 * BASE / 200 + 1;
+  const int x = lab_ab_to_xz(ify + adiv), z = lab_ab_to_xz(ify - bdiv);
+  const int ro = min(max((C[0] * x + C[1] * y + C[2] * z + 8192) >> 14, 0), 4095);
+  const int go = min(max((C[3] * x + C[4] * y + C[5] * z + 8192) >> 14, 0), 4095);
+  const int bo = min(max((C[6] * x + C[7] * y + C[8] * z + 8192) >> 14, 0), 4095);
+  r = t.invgamma[ro]; g = t.invgamma[go]; b = t.invgamma[bo];
+}
+template <int CH>
+struct IsLab { static constexpr bool value = (CH == CH_LAB_L || CH == CH_LAB_A || CH == CH_LAB_B); };
 
 // ---- helpers for 16-pixel (48 byte) groups ---------------------------------------------------
 struct Px16 {
@@ -35,7 +87,8 @@ __device__ __forceinline__ void px_set(Px16& r, int idx, int v) {
 }
 
 template <int CH>
-__device__ __forceinline__ int extract_channel(int b, int g, int r, const int* sdiv, const int* hdiv, bool hls_body = false) {
+__device__ __forceinline__ int extract_channel(int b, int g, int r, const int* sdiv, const int* hdiv, bool hls_body,
+                                               const LabSmem<IsLab<CH>::value>& lab) {
   if (CH == CH_B) return b;
   if (CH == CH_G) return g;
   if (CH == CH_R) return r;
@@ -49,6 +102,11 @@ __device__ __forceinline__ int extract_channel(int b, int g, int r, const int* s
     int H, L, S;
     bgr2hls_u8(b, g, r, hls_body, H, L, S);
     return CH == CH_HLS_H ? H : (CH == CH_HLS_L ? L : S);
+  }
+  if constexpr (IsLab<CH>::value) {
+    int L, A, Bc;
+    bgr2lab_u8(b, g, r, lab, L, A, Bc);
+    return CH == CH_LAB_L ? L : (CH == CH_LAB_A ? A : Bc);
   }
   int h, s, v;
   bgr2hsv_u8(b, g, r, sdiv, hdiv, h, s, v);
@@ -101,6 +159,8 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_frame_kernel(const uint8_t*
   constexpr bool HLS = (CH == CH_HLS_H || CH == CH_HLS_L || CH == CH_HLS_S);  // the only channels that depend on x
   __shared__ uint32_t sh[HIST_WARPS][256];
   __shared__ int s_sdiv[256], s_hdiv[256];
+  __shared__ LabSmem<IsLab<CH>::value> s_lab;
+  if constexpr (IsLab<CH>::value) s_lab.fill(true, false);
   for (int i = threadIdx.x; i < HIST_WARPS * 256; i += HIST_THREADS) (&sh[0][0])[i] = 0;
   if (CH == CH_H || CH == CH_S) {
     s_sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
@@ -119,13 +179,13 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_frame_kernel(const uint8_t*
       int xk = x0 + k;
       if (HLS && xk >= w) xk -= w;  // a 16-pixel group may straddle a row end
       int v = extract_channel<CH>(px_byte(q, 3 * k), px_byte(q, 3 * k + 1), px_byte(q, 3 * k + 2), s_sdiv, s_hdiv,
-                                  HLS && xk < hls_body_w);
+                                  HLS && xk < hls_body_w, s_lab);
       atomicAdd(&myh[v], 1u);
     }
   }
   for (size_t i = n16 * 16 + (size_t)blockIdx.x * HIST_THREADS + threadIdx.x; i < n_px; i += (size_t)gridDim.x * HIST_THREADS) {
     int v = extract_channel<CH>(p[3 * i], p[3 * i + 1], p[3 * i + 2], s_sdiv, s_hdiv,
-                                HLS && (int)(i % (size_t)w) < hls_body_w);
+                                HLS && (int)(i % (size_t)w) < hls_body_w, s_lab);
     atomicAdd(&myh[v], 1u);
   }
   hist_flush(sh, hist + (size_t)blockIdx.y * 256);
@@ -167,6 +227,9 @@ int k_histogram_frame(uwip_ctx* ctx, const uint8_t* d_bgr, int n, int w, int h, 
     case CH_HLS_H: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_H>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
     case CH_HLS_L: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_L>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
     case CH_HLS_S: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_HLS_S>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_LAB_L: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_LAB_L>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_LAB_A: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_LAB_A>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
+    case CH_LAB_B: UWIP_LAUNCH(ctx, "hist_frame", hist_frame_kernel<CH_LAB_B>, grid, HIST_THREADS, 0, d_bgr, n_px, d_hist, w, hbw); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
   return UWIP_OK;
@@ -277,7 +340,8 @@ int k_apply_lut_plane(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
 // one pixel of the histretch channel loop: (optionally) convert, LUT one channel, convert back
 template <int CH>
 __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint8_t* s_lut, bool use_lut, bool trunc_mode,
-                                              const int* sdiv, const int* hdiv, bool hls_body) {
+                                              const int* sdiv, const int* hdiv, bool hls_body,
+                                              const LabSmem<IsLab<CH>::value>& lab) {
   if (CH == CH_B) { if (use_lut) b = s_lut[b]; return; }
   if (CH == CH_G) { if (use_lut) g = s_lut[g]; return; }
   if (CH == CH_R) { if (use_lut) r = s_lut[r]; return; }
@@ -303,6 +367,17 @@ __device__ __forceinline__ void stretch_pixel(int& b, int& g, int& r, const uint
     hls2bgr_u8(H, L, S, b, g, r);
     return;
   }
+  if constexpr (IsLab<CH>::value) {  // transformation[2]: BGR2Lab / Lab2BGR
+    int L, A, Bc;
+    bgr2lab_u8(b, g, r, lab, L, A, Bc);
+    if (use_lut) {
+      if (CH == CH_LAB_L) L = s_lut[L];
+      if (CH == CH_LAB_A) A = s_lut[A];
+      if (CH == CH_LAB_B) Bc = s_lut[Bc];
+    }
+    lab2bgr_u8(L, A, Bc, lab, b, g, r);
+    return;
+  }
   int h, s, v;
   bgr2hsv_u8(b, g, r, sdiv, hdiv, h, s, v);
   if (use_lut) {
@@ -319,6 +394,8 @@ __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __r
                                                               int h, const uint8_t* __restrict__ lut, int use_lut, int body_w, int hls_body_w) {
   __shared__ uint8_t s_lut[256];
   __shared__ int s_sdiv[256], s_hdiv[256];
+  __shared__ LabSmem<IsLab<CH>::value> s_lab;
+  if constexpr (IsLab<CH>::value) s_lab.fill(true, true);
   s_lut[threadIdx.x] = use_lut ? lut[(size_t)blockIdx.y * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
   s_sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
   s_hdiv[threadIdx.x] = hsv_hdiv(threadIdx.x);
@@ -334,7 +411,7 @@ __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __r
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       int b = px_byte(q, 3 * k), g = px_byte(q, 3 * k + 1), r = px_byte(q, 3 * k + 2);
-      stretch_pixel<CH>(b, g, r, s_lut, use_lut, (x0 + k) < body_w, s_sdiv, s_hdiv, (x0 + k) < hls_body_w);
+      stretch_pixel<CH>(b, g, r, s_lut, use_lut, (x0 + k) < body_w, s_sdiv, s_hdiv, (x0 + k) < hls_body_w, s_lab);
       px_set(q, 3 * k, b);
       px_set(q, 3 * k + 1, g);
       px_set(q, 3 * k + 2, r);
@@ -344,7 +421,7 @@ __global__ void __launch_bounds__(256) apply_lut_frame_kernel(const uint8_t* __r
   for (size_t i = n16 * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n_px; i += (size_t)gridDim.x * 256) {
     int b = p[3 * i], g = p[3 * i + 1], r = p[3 * i + 2];
     int x = (int)(i % (size_t)w);
-    stretch_pixel<CH>(b, g, r, s_lut, use_lut, x < body_w, s_sdiv, s_hdiv, x < hls_body_w);
+    stretch_pixel<CH>(b, g, r, s_lut, use_lut, x < body_w, s_sdiv, s_hdiv, x < hls_body_w, s_lab);
     o[3 * i] = (uint8_t)b;
     o[3 * i + 1] = (uint8_t)g;
     o[3 * i + 2] = (uint8_t)r;
@@ -378,6 +455,9 @@ int k_apply_lut_frame(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
     case CH_HLS_H: AL(CH_HLS_H); break;
     case CH_HLS_L: AL(CH_HLS_L); break;
     case CH_HLS_S: AL(CH_HLS_S); break;
+    case CH_LAB_L: AL(CH_LAB_L); break;
+    case CH_LAB_A: AL(CH_LAB_A); break;
+    case CH_LAB_B: AL(CH_LAB_B); break;
     default: uwip_set_err(ctx, "bad channel %d", channel); return UWIP_ERR_INVALID;
   }
 #undef AL
@@ -479,6 +559,9 @@ static int letter_channel(char c) {
     case 'h': return CH_HLS_H;
     case 's': return CH_HLS_L;  // numChannel('s') == 1 and plane 1 of BGR2HLS is L
     case 'l': return CH_HLS_S;  // numChannel('l') == 2 == the S plane
+    case 'L': return CH_LAB_L;
+    case 'a': return CH_LAB_A;
+    case 'b': return CH_LAB_B;
   }
   return -1;
 }
@@ -494,10 +577,6 @@ int histretch_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, in
   for (const char* c = channels; *c; ++c) {
     int sp = uwip_num_space(*c);
     if (sp == -1) continue;  // "Option not recognized, skipping..."
-    if (sp == 3) {  // Lab
-      uwip_set_err(ctx, "channel letter '%c' (colour space %d) is not built yet (SURVEY 8f N2)", *c, sp);
-      return UWIP_ERR_UNSUPPORTED;
-    }
     int ch = letter_channel(*c);
     bool literal_hsv = (sp != 0 && order == UWIP_ORDER_LITERAL);  // literal order: the frame becomes its colour-space round trip
     if (!literal_hsv) {
