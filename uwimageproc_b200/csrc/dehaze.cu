@@ -750,7 +750,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -835,7 +835,7 @@ struct PolGF1a {
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false;
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -922,7 +922,7 @@ struct PolGF1b {
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -999,7 +999,7 @@ struct PolGF2a {
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false;
   typedef ExpShared Shared;
   struct Raw {};
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1186,6 +1186,20 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   // output quads of this strip
   const int tq0 = gg.HL / 4 + 1;
   const bool oact = (t >= tq0) && (t < tq0 + gg.SW / 4) && (gx < W);
+  // Everything the march loop needs to know about this thread's quad lives in ONE word (at 255 registers the compiler
+  // otherwise parks the individual flags and counts in local-memory spill slots and reloads them every row):
+  //   bits 28..31 cmask; bits 7c..7c+6 the horizontal pixel count of the window of column c, set for output quads only
+  //   (so "output quad" == low 7 bits non-zero).  Counts need 2r + 1 <= 127; wider windows recompute them per row.
+  const bool nx_packed = (2 * gg.r + 1) <= 127;
+  unsigned meta = cmask << 28;
+  if (oact) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      int x = gx + c;
+      int nx = (x < gg.W) ? min(x + gg.r, gg.W - 1) - max(x - gg.r, 0) + 1 : 0;
+      meta |= (unsigned)(nx_packed ? nx : 1) << (7 * c);
+    }
+  }
   const int rho = r >> 2;
   // addresses used by the window sums: the quads at -rho / +rho and the totals around them
   const int tlo = oact ? t - rho : 0, thi = oact ? t + rho : 0;
@@ -1254,12 +1268,15 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
         if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gx);
       }
       cp_async_commit();
-      if (cmask == 0xfu) {  // whole quad inside the image: straight-line code
-        if (enter) pol.template accum<+1, true>(curE, cmask, Vi, Vd);
-        if (leave) pol.template accum<-1, true>(curL, cmask, Vi, Vd);
+      unsigned cm = meta;  // opaque copy: keeps the four bit tests of the partial-quad path out of spill slots
+      if constexpr (P::META) asm("" : "+r"(cm) : "r"(yi));  // not volatile (free to schedule), tied to the row so that it stays in the loop
+      cm >>= 28;
+      if (cm == 0xfu) {  // whole quad inside the image: straight-line code
+        if (enter) pol.template accum<+1, true>(curE, cm, Vi, Vd);
+        if (leave) pol.template accum<-1, true>(curL, cm, Vi, Vd);
       } else if (qload) {
-        if (enter) pol.template accum<+1, false>(curE, cmask, Vi, Vd);
-        if (leave) pol.template accum<-1, false>(curL, cmask, Vi, Vd);
+        if (enter) pol.template accum<+1, false>(curE, cm, Vi, Vd);
+        if (leave) pol.template accum<-1, false>(curL, cm, Vi, Vd);
       }
     } else {
       mbar_wait(mbar, (unsigned)par);  // phase parity = march row parity
@@ -1331,7 +1348,9 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       if (t == NT) tma_rows(yin + 2);  // every worker has consumed the staged rows
     }
     // ---- window sums and the per-pixel work -----------------------------------------------------------
-    if (oact) {
+    unsigned mrow = meta;  // opaque per-row copy (see the definition of meta)
+    if constexpr (P::META) asm("" : "+r"(mrow) : "r"(yo));
+    if (P::META ? (mrow & 127u) != 0 : oact) {  // output quad
       pol.row_begin(yo, gx);
       // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
       // that trade loads for registers (INT_HALF) - two columns per half
@@ -1402,17 +1421,20 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
             }
           }
         }
+        const unsigned cm = mrow >> 28;
+        int gxo = gx;
+        if constexpr (P::META) asm("" : "+r"(gxo) : "r"(yo));
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-          int x = gx + 2 * h + cc;
-          if (x < W) {
-            // window pixel count, formed where it is used (a value kept across the loads above ends up in a spill slot)
+          const int c = 2 * h + cc;
+          if (cm & (1u << c)) {  // column gx + c is an image column
+            const int x = gxo + c;
             const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
-            const int nx = min(x + r, W - 1) - max(x - r, 0) + 1;
+            const int nx = nx_packed ? (int)((mrow >> (7 * c)) & 127u) : min(x + r, W - 1) - max(x - r, 0) + 1;
             pol.column(cc, yo, x, ny * nx, si[P::INT_HALF ? cc : 2 * h + cc], sd[cc]);
           }
         }
-        if (gx + 2 * h < W) pol.store_pair(yo, gx + 2 * h);
+        if (cm & (1u << (2 * h))) pol.store_pair(yo, gxo + 2 * h);
       }
     }
     if constexpr (!P::DBUF) __syncthreads();  // C (with two buffers the barriers A, B of the next row order the reuse)
