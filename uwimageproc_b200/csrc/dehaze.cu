@@ -750,7 +750,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 // GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
 struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = false;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -835,7 +835,7 @@ struct PolGF1a {
 // GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -922,7 +922,7 @@ struct PolGF1b {
 // GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
 struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true;
+  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = true;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -999,7 +999,7 @@ struct PolGF2a {
 // GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false;
+  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
   typedef ExpShared Shared;
   struct Raw {};
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1300,53 +1300,17 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
     if (t == NT) tma_rows(y_begin + 1);
   }
 
-  // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
-  for (int yin = y_begin; yin < y_end; ++yin) {
-    const int yo = yin - r;
-    if (yo < ys) {  // warm-up rows (uniform across the CTA)
-      if (!aux) acc(yin + 1);
-      if constexpr (!P::PREFETCH) {
-        __syncthreads();
-        if (t == NT) tma_rows(yin + 2);
-      }
-      continue;
-    }
-    // ---- publish the quad prefixes and totals -------------------------------------------------------
+  // named barrier 1: the workers ARRIVE (they do not wait) once their row is published, the auxiliary warp waits on it
+  auto bar_arrive_published = [&]() { asm volatile("bar.arrive 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
+  auto bar_wait_published = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
+  // named barrier 2 (plane readers): the workers arrive when they have consumed the staged rows, the TMA producer waits
+  auto bar_arrive_consumed = [&]() { asm volatile("bar.arrive 2, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
+  auto bar_wait_consumed = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
+  static_assert(P::DBUF || !P::DELAY, "the delayed window phase reads one published row while the next one is written");
+
+  // window sums and per-pixel work of output row yo (published and scanned during the previous loop iteration)
+  auto window_phase = [&](const int yo) {
     select_buffer(yo);
-    if (qact) {
-#pragma unroll
-      for (int k = 0; k < NI; k++) {
-        uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-        Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-        Gi[k * GP + t] = p3;
-      }
-#pragma unroll
-      for (int k = 0; k < ND; k++) {
-        double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-        Pd01[k * NT + t] = make_double2(p0, p1);
-        Pd2[k * NT + t] = p2;
-        Gd[k * GP + t] = p3;
-      }
-    }
-    __syncthreads();  // A
-    if (aux) {
-      // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
-      // the auxiliary warps
-      const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
-      constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
-#pragma unroll
-      for (int rd = 0; rd < RI + RD; rd++) {
-        if (rd % P::NAUX != aw) continue;
-        if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
-        else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
-      }
-    } else {
-      acc(yin + 1);
-    }
-    __syncthreads();  // B
-    if constexpr (!P::PREFETCH) {
-      if (t == NT) tma_rows(yin + 2);  // every worker has consumed the staged rows
-    }
     // ---- window sums and the per-pixel work -----------------------------------------------------------
     unsigned mrow = meta;  // opaque per-row copy (see the definition of meta)
     if constexpr (P::META) asm("" : "+r"(mrow) : "r"(yo));
@@ -1437,7 +1401,124 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
         if (cm & (1u << (2 * h))) pol.store_pair(yo, gxo + 2 * h);
       }
     }
-    if constexpr (!P::DBUF) __syncthreads();  // C (with two buffers the barriers A, B of the next row order the reuse)
+  };
+
+  if constexpr (P::DELAY) {
+    // One loop iteration = one output row, ONE CTA-wide barrier:
+    //   workers: publish(yo) | arrive 1 | add march row yin+1 | arrive 2 | window sums + per-pixel work of row yo-1 | barrier
+    //   aux:     wait 1 (published) | scan the quad totals of row yo | wait 2 (staging consumed) | TMA(yin+2)       | barrier
+    // The scan of row yo has the whole worker phase to finish and is consumed one iteration later, so the workers never
+    // wait for it; the published rows are double-buffered by row parity, which is what makes the delay possible.
+    // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
+    for (int yin = y_begin; yin <= y_end; ++yin) {  // the extra iteration runs the window phase of the last row
+      const int yo = yin - r;
+      if (yo < ys) {  // warm-up rows (uniform across the CTA)
+        if (!aux) acc(yin + 1);
+        if constexpr (!P::PREFETCH) {
+          __syncthreads();
+          if (t == NT) tma_rows(yin + 2);
+        }
+        continue;
+      }
+      const bool pub = yo < ye;  // uniform
+      if (pub) {
+        // ---- publish the quad prefixes and totals -------------------------------------------------------
+        select_buffer(yo);
+        if (qact) {
+  #pragma unroll
+          for (int k = 0; k < NI; k++) {
+            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+            Gi[k * GP + t] = p3;
+          }
+  #pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+            Pd01[k * NT + t] = make_double2(p0, p1);
+            Pd2[k * NT + t] = p2;
+            Gd[k * GP + t] = p3;
+          }
+        }
+      }
+      if (aux) {
+        if (pub) {
+          bar_wait_published();
+          // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
+          // the auxiliary warps
+          const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
+          constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
+  #pragma unroll
+          for (int rd = 0; rd < RI + RD; rd++) {
+            if (rd % P::NAUX != aw) continue;
+            if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
+            else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
+          }
+        }
+      } else {
+        if (pub) bar_arrive_published();
+        acc(yin + 1);
+        if constexpr (!P::PREFETCH) bar_arrive_consumed();
+        if (yo > ys) window_phase(yo - 1);
+      }
+      if constexpr (!P::PREFETCH) {
+        if (aux) {
+          bar_wait_consumed();             // every worker has consumed the staged rows:
+          if (t == NT) tma_rows(yin + 2);  // the next ones land while the workers are in their window phase
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
+    for (int yin = y_begin; yin < y_end; ++yin) {
+      const int yo = yin - r;
+      if (yo < ys) {  // warm-up rows (uniform across the CTA)
+        if (!aux) acc(yin + 1);
+        if constexpr (!P::PREFETCH) {
+          __syncthreads();
+          if (t == NT) tma_rows(yin + 2);
+        }
+        continue;
+      }
+      // ---- publish the quad prefixes and totals -------------------------------------------------------
+      select_buffer(yo);
+      if (qact) {
+  #pragma unroll
+        for (int k = 0; k < NI; k++) {
+          uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+          Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+          Gi[k * GP + t] = p3;
+        }
+  #pragma unroll
+        for (int k = 0; k < ND; k++) {
+          double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+          Pd01[k * NT + t] = make_double2(p0, p1);
+          Pd2[k * NT + t] = p2;
+          Gd[k * GP + t] = p3;
+        }
+      }
+      __syncthreads();  // A
+      if (aux) {
+        // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
+        // the auxiliary warps
+        const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
+        constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
+  #pragma unroll
+        for (int rd = 0; rd < RI + RD; rd++) {
+          if (rd % P::NAUX != aw) continue;
+          if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
+          else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
+        }
+      } else {
+        acc(yin + 1);
+      }
+      __syncthreads();  // B
+      if constexpr (!P::PREFETCH) {
+        if (t == NT) tma_rows(yin + 2);  // every worker has consumed the staged rows
+      }
+      window_phase(yo);
+      if constexpr (!P::DBUF) __syncthreads();  // C (with two buffers the barriers A, B of the next row order the reuse)
+    }
   }
   pol.finish();
 }
