@@ -754,11 +754,11 @@ struct PolGF1a {
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
+    double epsN_k;      // eps * range^2 (read at its use: a register held across the march ends up in a spill slot)
   };
   struct Raw { uint4 k; uint32_t m; };
   GfCommon g; Shared* sh; int Wp, H, f;
   const uint32_t* kq; const uint8_t* mg; float* ab;
-  double epsN_k;  // eps * range^2
   __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
     g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
     size_t n_pp = (size_t)Wp * H;
@@ -773,7 +773,7 @@ struct PolGF1a {
       double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
       sh->pT[c][k] = grid_round<28>((t < g.tmin) ? g.tmin : t);  // np.maximum(t, tmin) (NaN stays NaN), on the 2^-28 grid
     }
-    epsN_k = g.eps * range * range;
+    if (threadIdx.x == 0) sh->epsN_k = g.eps * range * range;
     __syncthreads();
   }
   // staging slot s (0..3 = 2 buffers x enter/leave) of this thread: one uint4 + one u32
@@ -818,7 +818,7 @@ struct PolGF1a {
   __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
     double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
     double M[6], Sd[3], A[6], rdet;
-    gf_build_M(si, N, epsN_k * N * N, M, Sd);
+    gf_build_M(si, N, *(volatile double*)&sh->epsN_k * N * N, M, Sd);
     gf_adjugate(M, A, rdet);
     double a[3], b;
     const int gq = x >> 2, c = x & 3;
@@ -1264,8 +1264,10 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       if (qload && leave) pol.stage_read(stage, 2 * par + 1, curL);
       const int yn = yi + 1, yln = yli + 1;
       if (qload && yn < y_end) {
-        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (par ^ 1), yn, gx);
-        if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gx);
+        int gxa = gx;  // opaque: the row addresses are formed from the (uniform) plane base here, not carried per thread
+        if constexpr (P::META) asm("" : "+r"(gxa) : "r"(yi));
+        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (par ^ 1), yn, gxa);
+        if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gxa);
       }
       cp_async_commit();
       unsigned cm = meta;  // opaque copy: keeps the four bit tests of the partial-quad path out of spill slots
@@ -1304,8 +1306,8 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   auto bar_arrive_published = [&]() { asm volatile("bar.arrive 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
   auto bar_wait_published = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
   // named barrier 2 (plane readers): the workers arrive when they have consumed the staged rows, the TMA producer waits
-  auto bar_arrive_consumed = [&]() { asm volatile("bar.arrive 2, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
-  auto bar_wait_consumed = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
+  auto bar_arrive_consumed = [&]() { asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory"); };
+  auto bar_wait_consumed = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); };
   static_assert(P::DBUF || !P::DELAY, "the delayed window phase reads one published row while the next one is written");
 
   // window sums and per-pixel work of output row yo (published and scanned during the previous loop iteration)
@@ -1457,14 +1459,17 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       } else {
         if (pub) bar_arrive_published();
         acc(yin + 1);
-        if constexpr (!P::PREFETCH) bar_arrive_consumed();
-        if (yo > ys) window_phase(yo - 1);
-      }
-      if constexpr (!P::PREFETCH) {
-        if (aux) {
-          bar_wait_consumed();             // every worker has consumed the staged rows:
-          if (t == NT) tma_rows(yin + 2);  // the next ones land while the workers are in their window phase
+        if constexpr (!P::PREFETCH) {
+          // plane readers: the LAST worker warp waits until every worker has consumed the staged rows (named barrier 2,
+          // workers only) and its first lane requests the next ones, which land during the window phase
+          if (t >= NT - 32) {
+            bar_wait_consumed();
+            if (t == NT - 32) tma_rows(yin + 2);
+          } else {
+            bar_arrive_consumed();
+          }
         }
+        if (yo > ys) window_phase(yo - 1);
       }
       __syncthreads();
     }
