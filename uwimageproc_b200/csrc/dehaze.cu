@@ -751,6 +751,7 @@ constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max thr
 struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = false;
+  static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -836,6 +837,7 @@ struct PolGF1a {
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
+  static constexpr int EARLY_ROW = 1, ROWST_BYTES = 0;  // row_begin's one 16-byte load goes out before the accumulate phase
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -923,6 +925,7 @@ struct PolGF1b {
 struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = true;
+  static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1000,6 +1003,7 @@ struct PolGF2a {
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
+  static constexpr int EARLY_ROW = 2, ROWST_BYTES = NT * 64;  // row_begin's four 16-byte loads are staged through shared memory (cp.async)
   typedef ExpShared Shared;
   struct Raw {};
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1026,6 +1030,25 @@ struct PolGF2b {
     yrow = __ldg(reinterpret_cast<const uint4*>(ycc + o));
     jb = __ldg(reinterpret_cast<const float4*>(J + o));
     jg = __ldg(reinterpret_cast<const float4*>(J + n_pp + o));
+  }
+  // the same four loads as asynchronous copies into this thread's staging slots, and their pick-up
+  __device__ __forceinline__ void row_prefetch(unsigned char* rs, int y, int gx) const {
+    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
+    uint4* slot = reinterpret_cast<uint4*>(rs) + threadIdx.x;
+    cp_async16(slot, kq + o);
+    cp_async16(slot + NT, ycc + o);
+    cp_async16(slot + 2 * NT, J + o);
+    cp_async16(slot + 3 * NT, J + n_pp + o);
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void row_pickup(const unsigned char* rs) {
+    cp_async_wait_all();
+    const uint4* slot = reinterpret_cast<const uint4*>(rs) + threadIdx.x;
+    krow = slot[0];
+    yrow = slot[NT];
+    uint4 a = slot[2 * NT], b = slot[3 * NT];
+    jb = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+    jg = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
   }
   __device__ __forceinline__ void column(int cc, int, int x, int Ncnt, const uint32_t*, const double* sd) {
     double invN = rcp_fast(u2d((uint32_t)Ncnt));
@@ -1132,7 +1155,8 @@ struct GfSmem {
   static constexpr size_t off_sh = buf_bytes * (P::DBUF ? 2 : 1);
   static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 127) & ~(size_t)127;  // quad blocks stay block-aligned
   static constexpr size_t off_bar = off_st + P::STAGE_BYTES;
-  static constexpr size_t bytes = off_bar + 16;
+  static constexpr size_t off_row = off_bar + 16;          // per-thread staging of row_begin's inputs (EARLY_ROW == 2)
+  static constexpr size_t bytes = off_row + P::ROWST_BYTES;
 };
 
 // Thread roles: threads 0..NT-1 are WORKERS (one quad of the strip each); the last warp is the AUXILIARY
@@ -1317,7 +1341,8 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
     unsigned mrow = meta;  // opaque per-row copy (see the definition of meta)
     if constexpr (P::META) asm("" : "+r"(mrow) : "r"(yo));
     if (P::META ? (mrow & 127u) != 0 : oact) {  // output quad
-      pol.row_begin(yo, gx);
+      if constexpr (P::EARLY_ROW == 0) pol.row_begin(yo, gx);
+      if constexpr (P::EARLY_ROW == 2) pol.row_pickup(smem_raw + L::off_row);
       // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
       // that trade loads for registers (INT_HALF) - two columns per half
       uint32_t si[P::INT_HALF ? 2 : 4][NIa];
@@ -1515,6 +1540,10 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
           else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
         }
       } else {
+        // plane readers that want it: the global loads of row yo's per-pixel inputs go out here, a whole accumulate phase
+        // (and barrier B) before their first use
+        if constexpr (P::EARLY_ROW == 1) { if (oact) pol.row_begin(yo, gx); }
+        if constexpr (P::EARLY_ROW == 2) { if (oact) pol.row_prefetch(smem_raw + L::off_row, yo, gx); }
         acc(yin + 1);
       }
       __syncthreads();  // B
@@ -1541,6 +1570,9 @@ static GfGeom gf_geometry(int W, int H, int r, int NT) {
   g.fast = (r % 4 == 0) ? 1 : 0;
   return g;
 }
+
+static_assert(GfSmem<PolGF2b>::bytes + 1024 <= (227 * 1024) / 2, "GF2b runs two CTAs per SM");
+static_assert(GfSmem<PolGF1a>::bytes <= 227 * 1024 && GfSmem<PolGF1b>::bytes <= 227 * 1024 && GfSmem<PolGF2a>::bytes <= 227 * 1024, "shared memory");
 
 template <class P>
 static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, int W, int H, int r) {
