@@ -752,6 +752,7 @@ struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = false;
   static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
+  static constexpr bool UNCOND_STAGE = true;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -837,6 +838,7 @@ struct PolGF1a {
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
+  static constexpr bool UNCOND_STAGE = false;
   static constexpr int EARLY_ROW = 1, ROWST_BYTES = 0;  // row_begin's one 16-byte load goes out before the accumulate phase
   struct Shared {
     double nrm[256];
@@ -926,6 +928,7 @@ struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = true;
   static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
+  static constexpr bool UNCOND_STAGE = false;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1003,6 +1006,7 @@ struct PolGF2a {
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
+  static constexpr bool UNCOND_STAGE = false;
   static constexpr int EARLY_ROW = 2, ROWST_BYTES = NT * 64;  // row_begin's four 16-byte loads are staged through shared memory (cp.async)
   typedef ExpShared Shared;
   struct Raw {};
@@ -1226,7 +1230,7 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
   }
   const int rho = r >> 2;
   // addresses used by the window sums: the quads at -rho / +rho and the totals around them
-  const int tlo = oact ? t - rho : 0, thi = oact ? t + rho : 0;
+  const int tlo_h = oact ? t - rho : 0, thi_h = oact ? t + rho : 0;  // policies without META keep them across the march
   // quads of this strip that lie inside the padded image: [tA, tB) (the guard quad 0 stays zero)
   const int tA = max(1, (gg.HL + 4 - xs) >> 2), tB = min(NQ, (gg.Wp - xs + gg.HL + 4) >> 2);
 
@@ -1284,8 +1288,10 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       // goes out now into the other buffer
       cp_async_wait_all();
       typename P::Raw curE, curL;
-      if (qload && enter) pol.stage_read(stage, 2 * par, curE);
-      if (qload && leave) pol.stage_read(stage, 2 * par + 1, curL);
+      // UNCOND_STAGE: read unconditionally (a slot that was not filled for this row is read but never used) - GF1a's
+      // conditionally assigned struct is otherwise kept in local memory by the compiler
+      if (P::UNCOND_STAGE || (qload && enter)) pol.stage_read(stage, 2 * par, curE);
+      if (P::UNCOND_STAGE || (qload && leave)) pol.stage_read(stage, 2 * par + 1, curL);
       const int yn = yi + 1, yln = yli + 1;
       if (qload && yn < y_end) {
         int gxa = gx;  // opaque: the row addresses are formed from the (uniform) plane base here, not carried per thread
@@ -1341,6 +1347,11 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
     unsigned mrow = meta;  // opaque per-row copy (see the definition of meta)
     if constexpr (P::META) asm("" : "+r"(mrow) : "r"(yo));
     if (P::META ? (mrow & 127u) != 0 : oact) {  // output quad
+      // META: the two shared-memory indices are formed from the thread index per row (held across the march they end up
+      // in spill slots)
+      int tq = t;
+      if constexpr (P::META) asm("" : "+r"(tq) : "r"(yo));
+      const int tlo = P::META ? tq - rho : tlo_h, thi = P::META ? tq + rho : thi_h;
       if constexpr (P::EARLY_ROW == 0) pol.row_begin(yo, gx);
       if constexpr (P::EARLY_ROW == 2) pol.row_pickup(smem_raw + L::off_row);
       // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
