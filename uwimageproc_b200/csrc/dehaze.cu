@@ -752,7 +752,7 @@ struct PolGF1a {
   static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = false;
   static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
-  static constexpr bool UNCOND_STAGE = true;
+  static constexpr bool EARLY_SCAN = false, UNCOND_STAGE = true;
   struct Shared {
     double pT[2][256];  // p_c as a function of the window-min k'
     FrameConst fc;
@@ -838,7 +838,7 @@ struct PolGF1a {
 struct PolGF1b {
   static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
-  static constexpr bool UNCOND_STAGE = false;
+  static constexpr bool EARLY_SCAN = true, UNCOND_STAGE = false;
   static constexpr int EARLY_ROW = 1, ROWST_BYTES = 0;  // row_begin's one 16-byte load goes out before the accumulate phase
   struct Shared {
     double nrm[256];
@@ -928,7 +928,7 @@ struct PolGF2a {
   static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = true;
   static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
-  static constexpr bool UNCOND_STAGE = false;
+  static constexpr bool EARLY_SCAN = false, UNCOND_STAGE = false;
   struct Shared { FrameConst fc; };
   struct Raw { uint4 y; float4 s; };
   GfCommon g; Shared* sh; int Wp, H, f;
@@ -1006,7 +1006,7 @@ struct PolGF2a {
 struct PolGF2b {
   static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
   static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
-  static constexpr bool UNCOND_STAGE = false;
+  static constexpr bool EARLY_SCAN = true, UNCOND_STAGE = false;
   static constexpr int EARLY_ROW = 2, ROWST_BYTES = NT * 64;  // row_begin's four 16-byte loads are staged through shared memory (cp.async)
   typedef ExpShared Shared;
   struct Raw {};
@@ -1523,22 +1523,49 @@ __global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) g
       }
       // ---- publish the quad prefixes and totals -------------------------------------------------------
       select_buffer(yo);
-      if (qact) {
+      if constexpr (P::EARLY_SCAN) {
+        // quad totals first: as soon as every worker has stored them (named barrier 1, the workers only arrive) the
+        // auxiliary warp starts its scan, while the workers go on with the quad prefixes and the next march row.
+        // The sums are exact, so (V0 + V2) + (V1 + V3) is the last element of the prefix chain bit for bit (and shares no
+        // subexpression with it that the compiler would keep in registers across the hand-off).
+        if (qact) {
   #pragma unroll
-        for (int k = 0; k < NI; k++) {
-          uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-          Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-          Gi[k * GP + t] = p3;
-        }
+          for (int k = 0; k < NI; k++) Gi[k * GP + t] = (Vi[0][k] + Vi[2][k]) + (Vi[1][k] + Vi[3][k]);
   #pragma unroll
-        for (int k = 0; k < ND; k++) {
-          double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-          Pd01[k * NT + t] = make_double2(p0, p1);
-          Pd2[k * NT + t] = p2;
-          Gd[k * GP + t] = p3;
+          for (int k = 0; k < ND; k++) Gd[k * GP + t] = (Vd[0][k] + Vd[2][k]) + (Vd[1][k] + Vd[3][k]);
         }
+        if (aux) bar_wait_published(); else bar_arrive_published();
+        if (qact) {
+  #pragma unroll
+          for (int k = 0; k < NI; k++) {
+            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+          }
+  #pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k];
+            Pd01[k * NT + t] = make_double2(p0, p1);
+            Pd2[k * NT + t] = p2;
+          }
+        }
+      } else {
+        if (qact) {
+    #pragma unroll
+          for (int k = 0; k < NI; k++) {
+            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
+            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
+            Gi[k * GP + t] = p3;
+          }
+    #pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
+            Pd01[k * NT + t] = make_double2(p0, p1);
+            Pd2[k * NT + t] = p2;
+            Gd[k * GP + t] = p3;
+          }
+        }
+        __syncthreads();  // A
       }
-      __syncthreads();  // A
       if (aux) {
         // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
         // the auxiliary warps
