@@ -396,10 +396,11 @@ def test_cpp_shims_on_device():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("radius", [3, 4, 7, 10, 16, 40])
+@pytest.mark.parametrize("radius", [3, 4, 7, 10, 16, 40, 63, 64, 65, 100, 160])
 def test_refined_transmission_other_radii(ctx, radius):
     """The guided-filter radius is a parameter of the ABI (the reference fixes r=40, BGDehaze.py:41): radii that
-    are multiples of 4 take the quad path, the others the scalar window path; both against the oracle."""
+    are multiples of 4 take the quad path, the others the scalar window path; windows wider than 127 pixels (r >= 64)
+    recompute the per-column pixel counts per row instead of unpacking them; all against the oracle."""
     fr = O.synth_frame(0x5EED0003, 2, 212, 118)   # width not a multiple of 4: pad columns are exercised too
     normI = O.normalize_frame(fr)
     for eps, tmin in [(1e-3, 0.2), (1e-2, 0.35)]:
