@@ -1,5 +1,5 @@
 // Drop-in replacement for modules/common/preprocessing.h of MecatronicaUSB/uwimageproc: the same
-// global-namespace signatures (preprocessing.h:38,66,109,112,115 and aclahe.cpp:58), implemented on
+// global-namespace signatures (preprocessing.h:38,66,109,112,115, aclahe.cpp:58 and videostrip.hpp:98,106), implemented on
 // libuwip.so (include/uwip.h) instead of OpenCV's CPU kernels.  A module that includes this header and
 // links preprocessing_uwip.cpp + libuwip.so in place of ../common/preprocessing.cpp needs no other change.
 #ifndef UWIP_SHIM_PREPROCESSING_H
@@ -26,6 +26,12 @@ int numSpace(char c);    // preprocessing.h:115
 
 // float aclaheEntropy(cv::Mat img)   (aclahe.cpp:58, 228-248)
 float aclaheEntropy(cv::Mat img);
+
+// float calcBlur(Mat frame) / float calcBlurGPU(Mat frame)   (modules/videostrip/include/videostrip.hpp:98,106;
+// videostrip.cpp:170-184, 39-60): standard deviation of the 8-bit Laplacian of the grey frame.  calcBlur's call
+// `Laplacian(grey, laplacian, grey.type(), CV_16S)` means aperture 3; calcBlurGPU asks cv::cuda for aperture 1.
+float calcBlur(cv::Mat frame);
+float calcBlurGPU(cv::Mat frame);
 
 // What the reference's "print and continue" becomes across an ABI: the status of the last shim call on
 // this thread (0 = UWIP_OK) and its text.  The reference signatures themselves stay void.

@@ -93,3 +93,15 @@ float aclaheEntropy(cv::Mat img) {
   shim_done(uwip_entropy_u8(ctx, img.data, img.cols, img.rows, (size_t)img.step, /*flavour: aclahe.cpp*/ 0, &e));
   return e;
 }
+
+// videostrip.cpp:170-184 (calcBlur) and :39-60 (calcBlurGPU): BGR frame in, float stdev out
+static float calc_blur_shim(const cv::Mat& frame, int aperture) {
+  uwip_ctx* ctx = shim_ctx();
+  float sd = 0.f;
+  if (!ctx) return sd;
+  if (frame.empty() || frame.type() != CV_8UC3) { shim_done(UWIP_ERR_INVALID); return sd; }
+  shim_done(uwip_calc_blur_bgr8(ctx, frame.data, (size_t)frame.step, frame.cols, frame.rows, aperture, &sd, nullptr, nullptr, 0));
+  return sd;
+}
+float calcBlur(cv::Mat frame) { return calc_blur_shim(frame, 3); }
+float calcBlurGPU(cv::Mat frame) { return calc_blur_shim(frame, 1); }
