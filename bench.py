@@ -205,7 +205,19 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # ... and whatever the environment (nccl.conf, a pod-level NCCL_DEBUG) still makes NCCL print while the
+        # communicator comes up goes to stderr: file descriptor 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     ctx = u.Context(local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
