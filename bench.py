@@ -135,6 +135,15 @@ def cpu_chain_fps(procs, w, h, frames_per_proc=1, first=0):
     return len(jobs) / dt, dt
 
 
+def chain_config(W, H, n):
+    """`config` of the bench line: the same dictionary for the CUDA arm and for the reference arm."""
+    fbytes = W * H * 3
+    return {"workload": "fused histretch(V,1/99)->aclahe(8x8,clip2)->bgdehaze(w15,r40,eps1e-3) chain on %dx%d bgr8 frames, "
+                        "batch of %d frames per GPU per step (BASELINE configs[3])" % (W, H, n),
+            "frames_per_gpu_per_step": n, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (n * fbytes / 1e9),
+            "sharding": "disjoint frame batches per rank, no collective on the data path"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -156,7 +165,7 @@ def run_reference(args):
         "impl": "reference", "metric": "chain_frames_per_s_4k", "value": fps4k, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": "fused histretch(V,1/99)->aclahe(8x8,clip2)->bgdehaze(w15,r40) chain, 3840x2160 bgr8 frames"},
+        "config": chain_config(args.width, args.height, args.frames),
         "cpu_baseline": {"value": fps4k, "unit": "frames/s", "cores": procs, "kind": "port",
                          "sample": "%d synthetic %dx%d frames per step on %d processes (cv2 for the OpenCV calls, numpy fp64 "
                                    "restatement for bgdehaze), scaled by pixel count to 3840x2160" % (procs, sw, sh, procs)},
@@ -329,10 +338,7 @@ def main():
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (histretch, aclahe) / int32+f64 (bgdehaze)", "data": "synthetic",
-        "config": {"workload": "fused histretch(V,1/99)->aclahe(8x8,clip2)->bgdehaze(w15,r40,eps1e-3) chain on %dx%d bgr8 frames, "
-                               "batch of %d frames per GPU per step (BASELINE configs[3])" % (W, H, n),
-                   "frames_per_gpu_per_step": n, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (n * fbytes / 1e9),
-                   "sharding": "disjoint frame batches per rank, no collective on the data path"},
+        "config": chain_config(W, H, n),
         "gpu_launches": launches,
         "chain_hbm": {"algo_bytes_per_frame": CHAIN_BPP * W * H, "achieved_GBps_per_gpu": chain_gbs, "frac_of_peak": chain_gbs / peak,
                       "roofline_fps_per_gpu": peak * 1e9 / (CHAIN_BPP * W * H)},
