@@ -306,7 +306,36 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
   s_nrm[tid] = (double)tid / (double)range;  // normI value of k' (main.py:17)
   // region [y0-7, y0+48+7) x [x0-7, x0+73) : 62 x 80 pixels (78 used + 2 for the vector loads).
   // thread = (column, row mod 3); the loads of several rows are issued before the first use
-  if (tid < 240) {
+  const bool words = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);  // rows start on 4-byte boundaries
+  if (words) {
+    // the 240 bytes of a region row come in as aligned 32-bit words (one coalesced request per row instead of 240 byte
+    // loads) into a raw staging area that borrows HX0 (free until the horizontal phase), then get unpacked from shared
+    uint32_t* RAW = HX0;  // [62][64] words
+    const int xa = max(x0 - WF_R, 0), xb = min(x0 - WF_R + 79, W - 1);  // first / last image column of the region
+    const int byte0 = (xa * 3) & ~3;
+    const int nw = ((xb * 3 + 2) >> 2) - (byte0 >> 2) + 1;             // <= 61
+#pragma unroll 4
+    for (int idx = tid; idx < WF_RH * 64; idx += 256) {
+      const int ry = idx >> 6, wi = idx & 63;
+      if (wi < nw) {
+        const int y = min(max(y0 - WF_R + ry, 0), H - 1);
+        RAW[idx] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * W * 3 + byte0) + wi);
+      }
+    }
+    __syncthreads();
+    if (tid < 240) {
+      const int rx = tid % 80, rr = tid / 80;
+      const int xc = min(max(x0 - WF_R + rx, 0), W - 1);
+      const uint8_t* rawb = reinterpret_cast<const uint8_t*>(RAW) + (xc * 3 - byte0);
+#pragma unroll 7
+      for (int ry = rr; ry < WF_RH; ry += 3) {
+        const uint8_t* p = rawb + ry * 256;
+        uint32_t b = p[0], g = p[1], r = p[2];
+        P0[ry * WF_PP + rx] = b | (g << 16);
+        P1[ry * WF_PP + rx] = r;
+      }
+    }
+  } else if (tid < 240) {
     const int rx = tid % 80, rr = tid / 80;
     const int xc = min(max(x0 - WF_R + rx, 0), W - 1);
     const uint8_t* col = img + (size_t)xc * 3;
