@@ -260,10 +260,11 @@ __global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __res
 }
 
 // ---- fast path: both windows 15x15 (the reference's only reachable configuration unless -w is given) ----
-// Tile 64 x 48 outputs, 256 threads.  The window max / min of a run of outputs is formed in registers by
+// Tile 64 x 32 outputs, 256 threads, three CTAs per SM (64 x 48 at two CTAs per SM measured 8 % slower).  The window max / min of a run of outputs is formed in registers by
 // doubling: m2[i] = op(p[i], p[i+1]), m4[i] = op(m2[i], m2[i+2]), m8[i] = op(m4[i], m4[i+4]),
 // m15[i] = op(m8[i], m8[i+7])  (4 ops per output instead of 14), on 16-bit pairs (VIMNMX.U16x2).
-constexpr int WF_TX = 64, WF_TY = 48, WF_R = 7, WF_RH = WF_TY + 2 * WF_R;   // 62 region rows
+constexpr int WF_TX = 64, WF_TY = 32, WF_R = 7, WF_RH = WF_TY + 2 * WF_R;   // region rows
+constexpr int WF_VR = WF_TY / 4, WF_CTAS = 3;  // output rows per vertical run (four runs of 64 columns); CTAs per SM
 constexpr int WF_PP = 84;   // region pitch in words: 78 used; 21 x 16 bytes (odd) -> conflict-free 16-byte loads down a column of rows
 constexpr int WF_HP = 68;   // pitch of the horizontal results: 17 x 16 bytes
 
@@ -288,15 +289,15 @@ __device__ __forceinline__ bool cand_less(int ai, double ad, unsigned aidx, int 
   return (ai < bi) || (ai == bi && ((ad < bd) || (ad == bd && aidx < bidx)));
 }
 
-__global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restrict__ src, int W, int H, int Wp,
+__global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* __restrict__ src, int W, int H, int Wp,
                                                           const FrameState* __restrict__ fs, uint32_t* __restrict__ kq,
                                                           uint8_t* __restrict__ mgp, ArgPartial* __restrict__ partials) {
   extern __shared__ __align__(16) uint32_t s_w[];
   __shared__ double s_nrm[256];
   __shared__ ArgPartial s_part[8];
-  uint32_t* P0 = s_w;                       // [62][84] (B | G<<16), replicate border
-  uint32_t* P1 = P0 + WF_RH * WF_PP;        // [62][84] R
-  uint32_t* HX0 = P1 + WF_RH * WF_PP;       // [62][68] horizontal max (B,G)
+  uint32_t* P0 = s_w;                       // [WF_RH][84] (B | G<<16), replicate border
+  uint32_t* P1 = P0 + WF_RH * WF_PP;        // [WF_RH][84] R
+  uint32_t* HX0 = P1 + WF_RH * WF_PP;       // [WF_RH][68] horizontal max (B,G)
   uint32_t* HX1 = HX0 + WF_RH * WF_HP;      // horizontal max R
   uint32_t* HN0 = HX1 + WF_RH * WF_HP;      // horizontal min (B,G)
   const int f = blockIdx.z, tid = threadIdx.x;
@@ -304,13 +305,13 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
   const int x0 = blockIdx.x * WF_TX, y0 = blockIdx.y * WF_TY;
   const int kmin = fs[f].kmin, range = (int)fs[f].kmax - kmin;
   s_nrm[tid] = (double)tid / (double)range;  // normI value of k' (main.py:17)
-  // region [y0-7, y0+48+7) x [x0-7, x0+73) : 62 x 80 pixels (78 used + 2 for the vector loads).
+  // region [y0-7, y0+WF_TY+7) x [x0-7, x0+73) : WF_RH x 80 pixels (78 used + 2 for the vector loads).
   // thread = (column, row mod 3); the loads of several rows are issued before the first use
   const bool words = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);  // rows start on 4-byte boundaries
   if (words) {
     // the 240 bytes of a region row come in as aligned 32-bit words (one coalesced request per row instead of 240 byte
     // loads) into a raw staging area that borrows HX0 (free until the horizontal phase), then get unpacked from shared
-    uint32_t* RAW = HX0;  // [62][64] words
+    uint32_t* RAW = HX0;  // [WF_RH][64] words
     const int xa = max(x0 - WF_R, 0), xb = min(x0 - WF_R + 79, W - 1);  // first / last image column of the region
     const int byte0 = (xa * 3) & ~3;
     const int nw = ((xb * 3 + 2) >> 2) - (byte0 >> 2) + 1;             // <= 61
@@ -382,28 +383,28 @@ __global__ void __launch_bounds__(256, 2) window15_kernel(const uint8_t* __restr
     h1[0] = make_uint4(o[0], o[1], o[2], o[3]); h1[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
   __syncthreads();
-  // vertical: thread = (column, run of 12 output rows)
+  // vertical: thread = (column, run of WF_VR output rows)
   const int x = tid & 63, run = tid >> 6;
   const int gx = x0 + x;
   ArgCand b0 = {0x7fffffff, 0.0, 0xffffffffu}, b1 = b0;
   int bp0 = -1, bp1 = -1;  // (max_R, max_X) pair of the current best: the same pair further down can never win (same D, larger index)
   if (gx < Wp) {
-    uint32_t p[26], mx0[12], mx1[12], mn0[12];
-    const int ry0 = run * 12;
+    uint32_t p[WF_VR + 14], mx0[WF_VR], mx1[WF_VR], mn0[WF_VR];
+    const int ry0 = run * WF_VR;
 #pragma unroll
-    for (int i = 0; i < 26; i++) p[i] = HX0[(ry0 + i) * WF_HP + x];
-    win15<12, true>(p, mx0);
+    for (int i = 0; i < WF_VR + 14; i++) p[i] = HX0[(ry0 + i) * WF_HP + x];
+    win15<WF_VR, true>(p, mx0);
 #pragma unroll
-    for (int i = 0; i < 26; i++) p[i] = HX1[(ry0 + i) * WF_HP + x];
-    win15<12, true>(p, mx1);
+    for (int i = 0; i < WF_VR + 14; i++) p[i] = HX1[(ry0 + i) * WF_HP + x];
+    win15<WF_VR, true>(p, mx1);
 #pragma unroll
-    for (int i = 0; i < 26; i++) p[i] = HN0[(ry0 + i) * WF_HP + x];
-    win15<12, false>(p, mn0);
+    for (int i = 0; i < WF_VR + 14; i++) p[i] = HN0[(ry0 + i) * WF_HP + x];
+    win15<WF_VR, false>(p, mn0);
     uint32_t* kqf = kq + (size_t)f * Wp * H;
     uint8_t* mgf = mgp + (size_t)f * Wp * H;
     const bool xt = (gx < WF_R) || (gx + WF_R >= W);
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
+    for (int i = 0; i < WF_VR; i++) {
       const int gy = y0 + ry0 + i;
       if (gy >= H) break;
       const size_t ppix = (size_t)gy * Wp + gx;
