@@ -1675,7 +1675,7 @@ static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, 
 // -------------------------------------------------------------------------------------------------
 // E: restored -> R8, I8 -> YCrCb joint min / max (BGDehaze.py:75-80); stores (Yi, Cri, Cbi, Yj)
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) exposure_minmax_kernel(GfCommon g, int W, int H, int Wp, double* dbg_restored) {
+__global__ void __launch_bounds__(256, 4) exposure_minmax_kernel(GfCommon g, int W, int H, int Wp, double* dbg_restored) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
@@ -1760,7 +1760,7 @@ __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) 
 }
 
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
-__global__ void __launch_bounds__(256) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256, 4) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
