@@ -145,3 +145,27 @@ def test_lab_tables_match_the_oracle():
     assert (arr("kLabInvGamma") == invgamma).all()
     assert [int(v) for v in re.search(r"LAB_FWD_COEFFS \{(.*?)\}", txt).group(1).split(",")] == list(fwd)
     assert [int(v) for v in re.search(r"LAB_INV_COEFFS \{(.*?)\}", txt).group(1).split(",")] == list(inv)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): ONE JSON line on stdout with the
+    contract's keys, the same `config` dictionary as the CUDA arm, no GPU needed."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "chain_frames_per_s_4k" and d["unit"] == "frames/s" and d["higher_is_better"]
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    sys.path.insert(0, root)
+    import bench
+
+    assert d["config"] == bench.chain_config(3840, 2160, 256)
