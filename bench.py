@@ -24,13 +24,17 @@ sys.path.insert(0, ROOT)
 W4K, H4K = 3840, 2160
 SEED = 0x5EED0004
 # algorithmic bytes per pixel of each pass (SURVEY.md 8d accounting; DESIGN.md "Kernels")
+# The canonical passes D-g (27) and D-h (30) both read the a,b planes of the third guided filter; here the filter is
+# applied once, inside dz_gf2b, which therefore carries D-g plus the a,b half of D-h (27 + 11 = 38) while dz_final
+# carries what is left of D-h (read refined S, J, I; write bgr8 = 19).  The chain total stays 188.
 ALGO_BPP = {
     "hist_frame": 3, "clahe_tilehist": 3, "clahe_apply": 6, "dz_window": 3, "dz_gf1a": 35, "dz_gf1b": 43,
-    "dz_exposure_minmax": 11, "dz_gf2a": 27, "dz_gf2b": 27, "dz_final": 30,
+    "dz_exposure_minmax": 11, "dz_gf2a": 27, "dz_gf2b": 38, "dz_final": 19,
     # helper passes outside the canonical accounting (their bytes are extra traffic, counted as 0 algorithmic)
     "dz_splane": 0,
 }
 CHAIN_BPP = 188
+assert sum(ALGO_BPP.values()) == CHAIN_BPP
 
 
 def measured_peak():
@@ -113,6 +117,33 @@ def _cpu_chain_one(args):
     return time.perf_counter() - t0, int(out.sum())
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the first-touch placement of its pinned host buffers) to the CPUs of the NUMA
+    node the GPU hangs off.  Returns a description for the bench line; silently does nothing when the box does not
+    expose the topology (single-node boxes report node -1 / 0 for every device)."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if node < 0 or len(nodes) < 2:
+            return {"node": node, "nodes": len(nodes), "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"node": node, "nodes": len(nodes), "bound": bool(cpus), "cpus": len(cpus)}
+    except Exception as e:  # topology files missing in the container
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def np_ascontig(a):
     import numpy as np
 
@@ -165,7 +196,9 @@ def run_reference(args):
         "impl": "reference", "metric": "chain_frames_per_s_4k", "value": fps4k, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": chain_config(args.width, args.height, args.frames),
+        "config": dict(chain_config(args.width, args.height, args.frames),
+                       reference_sample="each step = %d synthetic %dx%d frames (1/16 of a 4K frame each) through the CPU chain on %d "
+                                        "processes, frames/s scaled by pixel count to 3840x2160" % (procs, sw, sh, procs)),
         "cpu_baseline": {"value": fps4k, "unit": "frames/s", "cores": procs, "kind": "port",
                          "sample": "%d synthetic %dx%d frames per step on %d processes (cv2 for the OpenCV calls, numpy fp64 "
                                    "restatement for bgdehaze), scaled by pixel count to 3840x2160" % (procs, sw, sh, procs)},
@@ -173,6 +206,64 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: a stream of frames, contiguous frame ranges per GPU, one pass
+# ------------------------------------------------------------------------------------------------
+def run_stream(ctx, stream, dist, rank, world, total, batch, W, H, params, barrier):
+    """Each rank generates its frame range on the device in batches (the stream does not fit one GPU at once), runs the
+    chain once over it and keeps one checksum per frame; the checksums are gathered in stream order and compared with
+    a single-GPU recomputation of a sample of frames taken from every rank's range (rank 0)."""
+    import hashlib
+
+    import numpy as np
+    import torch
+
+    from uwimageproc_b200 import shard
+
+    first, count = shard.frame_range(rank, world, total)
+    sums = np.empty(count, np.uint64)
+    nan = 0
+    with torch.cuda.stream(stream):
+        d_in = torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty_like(d_in)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for f, nb in shard.batches(first, count, batch):
+            ctx.synth_dev(d_in, SEED + 1, f, nb, W, H)      # configs[4] uses seed 0x5EED0005
+            ctx.chain_dev(d_in, d_out, nb, W, H, params)
+            sums[f - first:f - first + nb] = ctx.checksum_dev(d_out, nb, W, H)
+            nan += int((np.asarray(ctx.last_frame_flags(nb)) != 0).sum())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, float(nan)], dtype=torch.float64, device="cuda")
+    if dist:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_max, nan_all = float(tmax[0].item()), int(t[1].item())
+    else:
+        ms_max, nan_all = ms, nan
+    allsums = shard.gather_checksums(sums, rank, world, total, dist, device="cuda")
+    res = None
+    if rank == 0:
+        # single-GPU recomputation of sampled frames (every rank's range contributes) on this rank
+        sample = sorted(set(int(v) for v in np.linspace(0, total - 1, num=min(total, 64)).round()))
+        ok = True
+        with torch.cuda.stream(stream):
+            for f in sample:
+                ctx.synth_dev(d_in, SEED + 1, f, 1, W, H)
+                ctx.chain_dev(d_in, d_out, 1, W, H, params)
+                ok = ok and (int(ctx.checksum_dev(d_out, 1, W, H)[0]) == int(allsums[f]))
+        res = {"frames": total, "stream_fps": total / (ms_max / 1000.0), "ms": ms_max, "includes": "on-device generation of the frames and "
+               "the per-frame checksum kernel", "frames_per_rank": count, "batch": batch, "nan_frames": nan_all,
+               "crc_equal": bool(ok), "crc_sampled_frames": len(sample),
+               "crc_digest": hashlib.sha1(np.ascontiguousarray(allsums).tobytes()).hexdigest()[:16],
+               "crc_digest_note": "sha1 over the per-frame checksums in stream order: equal digests at every GPU count = equal frames"}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -187,7 +278,11 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--stream", type=int, default=0, help="BASELINE configs[4]: one pass over a stream of this many frames, "
+                                                           "contiguous frame ranges per rank, per-frame checksums gathered")
+    ap.add_argument("--copy-ceiling", action="store_true", help="also time the bare H2D + D2H copies of the e2e step (no kernels)")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -207,6 +302,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libuwip has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         # the contract is ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
@@ -265,6 +361,12 @@ def main():
         prof = {k: ctx.profile_read(k) for k in ALGO_BPP}
         ctx.profile(False)
         sums = ctx.checksum_dev(d_out, min(n, 4), W, H)
+        # frames whose result is the reference's NaN frame (S = 0/0 somewhere): the chain writes zeros for them
+        nan_frames = int((np.asarray(ctx.last_frame_flags(n)) != 0).sum())
+
+    stream_res = None
+    if args.stream > 0:
+        stream_res = run_stream(ctx, stream, dist, rank, world, args.stream, n, W, H, params, barrier)
 
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist:
@@ -290,7 +392,23 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         same = bool((h_out[: min(n, 4)].numpy() == d_out[: min(n, 4)].cpu().numpy()).all())
         e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "frames/s", "h2d_bytes_per_step": n * fbytes,
-               "d2h_bytes_per_step": n * fbytes, "steps": args.e2e_steps, "matches_device_path": same}
+               "d2h_bytes_per_step": n * fbytes, "steps": args.e2e_steps, "matches_device_path": same, "numa": numa}
+        if args.copy_ceiling:
+            # the same bytes with no kernel in between: what the host side of the box can move with `world` ranks copying at once
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                d_in.copy_(h_in, non_blocking=True)
+                h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+            tc = torch.tensor([dtc], dtype=torch.float64, device="cuda")
+            if dist:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            ceil_fps = world * n * args.e2e_steps / float(tc.item())
+            e2e["copy_ceiling"] = {"frames_per_s": ceil_fps, "GBps_per_rank_each_way": n * fbytes * args.e2e_steps / float(tc.item()) / 1e9,
+                                   "e2e_frac_of_ceiling": e2e["value"] / ceil_fps,
+                                   "what": "H2D of the step's inputs and D2H of its outputs on one stream, all ranks at once, no kernels"}
 
     if rank != 0:
         if dist:
@@ -338,13 +456,17 @@ def main():
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (histretch, aclahe) / int32+f64 (bgdehaze)", "data": "synthetic",
-        "config": chain_config(W, H, n),
+        "config": dict(chain_config(W, H, n), nan_frames_per_step=nan_frames,
+                       nan_frames="frames of the batch whose reference result is all-NaN (S = 0/0 where Yi = Yj = 0, SURVEY 8a-D9): "
+                                  "flagged and written as zeros; they run the same kernels as every other frame"),
         "gpu_launches": launches,
         "chain_hbm": {"algo_bytes_per_frame": CHAIN_BPP * W * H, "achieved_GBps_per_gpu": chain_gbs, "frac_of_peak": chain_gbs / peak,
                       "roofline_fps_per_gpu": peak * 1e9 / (CHAIN_BPP * W * H)},
         "roofline": roofline, "kernels": kern, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
         "checksums": [int(s) for s in sums],
     }
+    if stream_res is not None:
+        line["stream"] = stream_res
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

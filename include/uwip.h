@@ -132,6 +132,12 @@ int uwip_gaussian_blur3_u8(uwip_ctx* ctx, const uint8_t* src, size_t src_pitch, 
 int uwip_clahe_entropy_sweep_u8(uwip_ctx* ctx, const uint8_t* plane, int width, int height,
                                 size_t pitch, int tiles, const double* clips, int n_clips,
                                 int flavour, float* entropies);
+/* the whole sweep of aclahe.cpp:160-193 / ACLAHE.py:20-47 in one call: n_frames device planes x n_grids square grids
+ * (the reference's 2, 4, 8, 16, 32) x n_clips clip limits -> entropies [n_frames][n_grids][n_clips] (HOST pointer; the
+ * 49-point knee search on them stays on the host like the reference's scipy calls).  Synchronises the stream. */
+int uwip_clahe_entropy_sweep_u8_dev(uwip_ctx* ctx, const uint8_t* d_planes, int n_frames, int width, int height,
+                                    const int* grids, int n_grids, const double* clips, int n_clips,
+                                    int flavour, float* entropies);
 /* frame wrapper aclahe.cpp:152-154 + the stubbed tail :214-218: BGR->HSV, CLAHE on V, HSV->BGR */
 int uwip_aclahe_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t src_pitch, uint8_t* dst,
                      size_t dst_pitch, int width, int height, double clip, int tiles_x,
@@ -150,6 +156,14 @@ typedef struct uwip_dehaze_params {
 } uwip_dehaze_params;
 void uwip_dehaze_defaults(uwip_dehaze_params* p);
 
+/* boxfilter(I, r)  guidedfilter.py:23-51: (2r+1)^2 window SUM of a float64 plane, windows truncated at the borders
+ * (what cv2.boxFilter(normalize=False, BORDER_CONSTANT) computes).  Stage entry for parity; direct sums. */
+int uwip_boxfilter_f64(uwip_ctx* ctx, const double* src, int width, int height, int r, double* dst);
+/* guided_filter(I, p, r, eps)  guidedfilter.py:54-103 for a guide of the form I = guide8 / range, guide8 an 8-bit
+ * three-channel image (every guide on the path is one: normI of main.py:17, normYiCrCb of BGDehaze.py:77-80);
+ * p float64 in [0, 1.6] (held on a 2^-28 grid), q float64.  Runs the same two marches as the chain's filters. */
+int uwip_guided_filter_u8(uwip_ctx* ctx, const uint8_t* guide, size_t pitch, int width, int height,
+                          int range, const double* p, int r, double eps, double* q);
 /* Background_light(normI, w)  BGDehaze.py:14-26 on the frame normalised as main.py:17.
  * Tie rule: first flat index of the minimum.  B in B,G,R order. */
 int uwip_background_light_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t pitch, int width,

@@ -357,6 +357,33 @@ def test_chain_full_size_properties(ctx):
     assert (ctx.aclahe(a, 2.0, (8, 8)) == O.aclahe_frame(a, 2.0, 8, 8)).all()
 
 
+def test_chain_4k_against_oracle(ctx):
+    """The headline configuration itself (BASELINE configs[3]: 3840x2160, seed 0x5EED0004 - frames 0 and 1 are the first
+    two frames bench.py processes) against the fp64 oracle: 8-bit output <= 1 LSB, refined transmission <= 1e-5 relative.
+    The oracle needs about half a minute per 4K frame."""
+    W, H = 3840, 2160
+    frames = np.stack([O.synth_frame(0x5EED0004, f, W, H) for f in (0, 1)])
+    got = ctx.chain(frames)
+    flags = ctx.last_frame_flags(2)
+    checked = 0
+    for i in range(2):
+        head = O.aclahe_frame(O.histretch_frame(frames[i], "V", 1, 99), 2.0, 8, 8)
+        st = {}
+        ref, ref8 = O.bgdehaze_frame(head, 15, st)
+        assert bool(flags[i] & 1) == bool(np.isnan(ref).any()), i
+        d = np.abs(got[i].astype(int) - ref8.astype(int))
+        assert d.max() <= 1, (i, d.max())
+        assert (d > 0).mean() < 0.02
+        if i == 0:
+            # float stage at full size: refined t of the frame the dehaze stage sees
+            assert (ctx.aclahe(ctx.histretch(frames[i], "V", 1, 99), 2.0, (8, 8)) == head).all()
+            rb, rg = ctx.refined_transmission(head)
+            assert (np.abs(rb - st["t_blue"]) / np.abs(st["t_blue"])).max() < 1e-5
+            assert (np.abs(rg - st["t_green"]) / np.abs(st["t_green"])).max() < 1e-5
+        checked += 1
+    assert checked == 2
+
+
 # ---- frame-batch sharding (SURVEY 8e): ranks are emulated one after the other on one GPU ------------------------
 def test_sharded_stream_equals_single_gpu(ctx):
     import torch

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libuwip.so")
+LIB_PATH = os.environ.get("UWIP_LIB") or os.path.join(HERE, "libuwip.so")  # UWIP_LIB: a build variant under test (scratch/variants.py)
 
 UWIP_OK = 0
 
@@ -64,10 +64,13 @@ SIGNATURES = {
     "uwip_entropy_u8": (_i, [_P, _u8p, _i, _i, _sz, _i, C.POINTER(C.c_float)]),
     "uwip_gaussian_blur3_u8": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i]),
     "uwip_clahe_entropy_sweep_u8": (_i, [_P, _u8p, _i, _i, _sz, _i, C.POINTER(_d), _i, _i, C.POINTER(C.c_float)]),
+    "uwip_clahe_entropy_sweep_u8_dev": (_i, [_P, _u8p, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_d), _i, _i, C.POINTER(C.c_float)]),
     "uwip_aclahe_bgr8": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i, _d, _i, _i, _i]),
     "uwip_aclahe_bgr8_dev": (_i, [_P, _u8p, _u8p, _i, _i, _i, _d, _i, _i, _i]),
     "uwip_dehaze_defaults": (None, [C.POINTER(DehazeParams)]),
     "uwip_chain_defaults": (None, [C.POINTER(ChainParams)]),
+    "uwip_boxfilter_f64": (_i, [_P, _P, _i, _i, _i, _P]),
+    "uwip_guided_filter_u8": (_i, [_P, _u8p, _sz, _i, _i, _i, _P, _i, _d, _P]),
     "uwip_background_light_bgr8": (_i, [_P, _u8p, _sz, _i, _i, _i, C.POINTER(_d), C.POINTER(C.c_int64)]),
     "uwip_transmission_bgr8": (_i, [_P, _u8p, _sz, _i, _i, _i, _P, _P]),
     "uwip_refined_transmission_bgr8": (_i, [_P, _u8p, _sz, _i, _i, C.POINTER(DehazeParams), _P, _P]),

@@ -135,6 +135,17 @@ class Context:
             out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
+    def clahe_entropy_sweep_dev(self, d_planes, n, width, height, grids, clips, flavour="py"):
+        """n device planes x grids x clips -> float32 [n][len(grids)][len(clips)] (one pixel pass per grid)."""
+        grids = np.ascontiguousarray(grids, dtype=np.int32)
+        clips = np.ascontiguousarray(clips, dtype=np.float64)
+        out = np.empty((n, len(grids), len(clips)), np.float32)
+        self._ck(self.lib.uwip_clahe_entropy_sweep_u8_dev(
+            self.h, _ptr(d_planes), n, width, height, grids.ctypes.data_as(C.POINTER(C.c_int)), len(grids),
+            clips.ctypes.data_as(C.POINTER(C.c_double)), len(clips), 0 if flavour == "cpp" else 1,
+            out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def aclahe(self, frame, clip=2.0, tiles=(8, 8), hsv_round="cv2"):
         f = _frame(frame)
         out = np.empty(f.shape, np.uint8)
@@ -159,6 +170,24 @@ class Context:
         tg = np.empty(f.shape[:2], np.float64)
         self._ck(self.lib.uwip_transmission_bgr8(self.h, _ptr(f), f.strides[0], f.shape[1], f.shape[0], int(window), _ptr(tb), _ptr(tg)))
         return tb, tg
+
+    def boxfilter(self, plane, r):
+        a = np.ascontiguousarray(plane, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("expected an H x W float64 plane")
+        out = np.empty(a.shape, np.float64)
+        self._ck(self.lib.uwip_boxfilter_f64(self.h, _ptr(a), a.shape[1], a.shape[0], int(r), _ptr(out)))
+        return out
+
+    def guided_filter_u8(self, guide8, rng, p, r=40, eps=1e-3):
+        g = _frame(guide8)
+        pp = np.ascontiguousarray(p, dtype=np.float64)
+        if pp.shape != g.shape[:2]:
+            raise ValueError("p must be H x W")
+        out = np.empty(pp.shape, np.float64)
+        self._ck(self.lib.uwip_guided_filter_u8(self.h, _ptr(g), g.strides[0], g.shape[1], g.shape[0], int(rng), _ptr(pp), int(r),
+                                                float(eps), _ptr(out)))
+        return out
 
     def refined_transmission(self, frame, params=None):
         f = _frame(frame)
@@ -231,6 +260,9 @@ class Context:
     def aclahe_dev(self, d_src, d_dst, n, width, height, clip=2.0, tiles=(8, 8), hsv_round="cv2"):
         self._ck(self.lib.uwip_aclahe_bgr8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, float(clip), tiles[0], tiles[1],
                                                HSV_ROUND[hsv_round]))
+
+    def clahe_dev(self, d_src, d_dst, n, width, height, clip=40.0, tiles=(8, 8)):
+        self._ck(self.lib.uwip_clahe_u8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, float(clip), int(tiles[0]), int(tiles[1])))
 
     def bgdehaze_dev(self, d_src, d_dst, n, width, height, params=None):
         p = params or self.dehaze_params()

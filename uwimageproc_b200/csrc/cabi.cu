@@ -363,6 +363,12 @@ int uwip_clahe_entropy_sweep_u8(uwip_ctx* ctx, const uint8_t* plane, int w, int 
   UWIP_CHECK(stage_in(ctx, SLOT_STAGE_IN, plane, pitch, w, h, 1, &d));
   return clahe_entropy_sweep_dev(ctx, d, w, h, tiles, clips, n_clips, flavour, entropies);
 }
+int uwip_clahe_entropy_sweep_u8_dev(uwip_ctx* ctx, const uint8_t* d_planes, int n, int w, int h, const int* grids, int n_grids,
+                                    const double* clips, int n_clips, int flavour, float* entropies) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, d_planes && grids && clips && entropies && (flavour == 0 || flavour == 1), "bad argument");
+  return clahe_entropy_sweep_batch_dev(ctx, d_planes, n, w, h, grids, n_grids, clips, n_clips, flavour, entropies);
+}
 int uwip_aclahe_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty,
                          int hsv_round) {
   CTX_GUARD(ctx);
@@ -492,6 +498,41 @@ int uwip_bgdehaze_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t sp, uint8_t* ds
   CTX_GUARD(ctx);
   UWIP_REQUIRE(ctx, dst8, "null output");
   return dehaze_host(ctx, src, sp, w, h, p, 0, dst8, dp, nullptr, nullptr, nullptr, nullptr, nullptr, out_f64);
+}
+
+int uwip_boxfilter_f64(uwip_ctx* ctx, const double* src, int w, int h, int r, double* dst) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, src && dst && w >= 1 && h >= 1 && r >= 0, "bad argument");
+  const size_t n_px = (size_t)w * h;
+  double* d = (double*)uwip_slot(ctx, SLOT_F64OUT, n_px * 8 * 3);
+  if (!d) return UWIP_ERR_NOMEM;
+  UWIP_CUDA(ctx, cudaMemcpyAsync(d, src, n_px * 8, cudaMemcpyHostToDevice, ctx->stream));
+  UWIP_CHECK(boxfilter_f64_dev(ctx, d, d + n_px, d + 2 * n_px, w, h, r));
+  UWIP_CUDA(ctx, cudaMemcpyAsync(dst, d + 2 * n_px, n_px * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UWIP_OK;
+}
+int uwip_guided_filter_u8(uwip_ctx* ctx, const uint8_t* guide, size_t pitch, int w, int h, int range, const double* p, int r, double eps,
+                          double* q) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, guide && p && q, "null argument");
+  uint8_t* d_g;
+  UWIP_CHECK(stage_in(ctx, SLOT_STAGE_IN, guide, pitch, w, h, 3, &d_g));
+  const size_t n_px = (size_t)w * h;
+  double* d = (double*)uwip_slot(ctx, SLOT_F64OUT, n_px * 8 * 2);
+  FrameState* fs = frame_state_get(ctx, 1);
+  if (!d || !fs) return UWIP_ERR_NOMEM;
+  UWIP_CUDA(ctx, cudaMemcpyAsync(d, p, n_px * 8, cudaMemcpyHostToDevice, ctx->stream));
+  UWIP_CHECK(guided_filter_u8_dev(ctx, d_g, d, d + n_px, w, h, range, r, eps, fs));
+  FrameState* hs = (FrameState*)ctx->pinned;
+  UWIP_CUDA(ctx, cudaMemcpyAsync(hs, fs, sizeof(FrameState), cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaMemcpyAsync(q, d + n_px, n_px * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hs->nan_flag & 2u) {
+    uwip_set_err(ctx, "uwip_guided_filter_u8: p must lie in [0, 1.6] (the signals of the path do: transmission <= 1, exposure ratio <= 1.54)");
+    return UWIP_ERR_INVALID;
+  }
+  return UWIP_OK;
 }
 
 static int32_t* flags_get(uwip_ctx* ctx, int n) {

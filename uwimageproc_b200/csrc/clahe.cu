@@ -7,6 +7,9 @@
 // (2) clip + redistribute + block prefix scan -> per-tile LUT, (3) bilinear blend of four tile LUTs,
 // fused with the BGR<->HSV conversions (and, in the chain, with the histretch LUT in front and the
 // dehaze min/max reduction behind).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 constexpr int TH_THREADS = 256;
@@ -404,68 +407,155 @@ int aclahe_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   return clahe_common(ctx, d_src, d_dst, n, w, h, clip, tx, ty, true, hsv_round, d_prelut, fs);
 }
 
-// ---- entropy sweep over clip limits for one grid -----------------------------------
-// Tile histograms do not depend on the clip limit: build them once, derive one LUT set per clip
-// limit, then ONE pixel pass accumulates the histogram of every CLAHE output without writing images.
+// ---- entropy sweep over clip limits (aclahe.cpp:160-193, ACLAHE.py:20-47) ---------------------
+// Tile histograms do not depend on the clip limit: build them once per grid, derive one LUT set per clip limit, then ONE
+// pixel pass per grid accumulates the histogram of every CLAHE output without writing images.
+//
+// The pixel pass works per INTERPOLATION CELL: all pixels whose four neighbouring tiles are the same (t1x, t2x, t1y, t2y).
+// A CTA owns a band of rows of one cell of one frame: the LUT sets of the four tiles for every clip limit are staged in
+// shared memory as uchar4 (l11, l12, l21, l22) per (clip, value) - 4 x 51 x 256 B = 52 KB, the figure of SURVEY 8f - so
+// one 32-bit shared load feeds a blend; the output histograms of the band ([n_cl][256] u32, another 52 KB) are
+// accumulated in shared memory and flushed once.  Pixels come in as 32-bit words (4 per load).
 constexpr int SW_MAX_CL = 64;
-__global__ void __launch_bounds__(256) sweep_hist_kernel(const uint8_t* __restrict__ src, TileGeom g, int rows_per,
-                                                         const uint8_t* __restrict__ lut /*[tile][n_cl][256]*/, int n_cl,
-                                                         uint32_t* __restrict__ out_hist /*[n_cl][256]*/) {
-  extern __shared__ uint32_t s_hist[];  // [n_cl][256]
-  for (int i = threadIdx.x; i < n_cl * 256; i += 256) s_hist[i] = 0;
+constexpr int SW_THREADS = 256;
+__global__ void __launch_bounds__(SW_THREADS, 2) sweep_cell_kernel(const uint8_t* __restrict__ src, TileGeom g, int band_rows, int bands,
+                                                                   const uint8_t* __restrict__ lut /*[frame][tile][n_cl][256]*/, int n_cl,
+                                                                   uint32_t* __restrict__ out_hist /*[frame][n_cl][256]*/) {
+  extern __shared__ __align__(16) uint32_t s_sw[];
+  uint32_t* s_lut = s_sw;                 // [n_cl][256] packed (l11, l12, l21, l22)
+  uint32_t* s_hist = s_sw + n_cl * 256;   // [n_cl][256]
+  const int f = blockIdx.z;
+  const int cell = blockIdx.x / bands, band = blockIdx.x - cell * bands;
+  const int cx = cell % (g.tx + 1), cy = cell / (g.tx + 1);   // cell index = floor(coordinate / tile - 0.5) + 1
+  const int t1x = max(cx - 1, 0), t2x = min(cx, g.tx - 1), t1y = max(cy - 1, 0), t2y = min(cy, g.ty - 1);
+  const uint8_t* flut = lut + (size_t)f * g.tx * g.ty * n_cl * 256;
+  const uint8_t* L11 = flut + (size_t)(t1y * g.tx + t1x) * n_cl * 256;
+  const uint8_t* L12 = flut + (size_t)(t1y * g.tx + t2x) * n_cl * 256;
+  const uint8_t* L21 = flut + (size_t)(t2y * g.tx + t1x) * n_cl * 256;
+  const uint8_t* L22 = flut + (size_t)(t2y * g.tx + t2x) * n_cl * 256;
+  for (int i = threadIdx.x; i < n_cl * 256; i += SW_THREADS) {
+    s_lut[i] = (uint32_t)__ldg(L11 + i) | ((uint32_t)__ldg(L12 + i) << 8) | ((uint32_t)__ldg(L21 + i) << 16) | ((uint32_t)__ldg(L22 + i) << 24);
+    s_hist[i] = 0;
+  }
   __syncthreads();
-  int y0 = blockIdx.x * rows_per, y1 = min(y0 + rows_per, g.H);
-  float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
-  int total = (y1 - y0) * g.W;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    int ry = i / g.W, x = i - ry * g.W, y = y0 + ry;
-    Interp iy = interp_coord(y, inv_th, g.ty), ix = interp_coord(x, inv_tw, g.tx);
-    int v = src[(size_t)y * g.W + x];
-    const uint8_t* p11 = lut + ((size_t)(iy.t1 * g.tx + ix.t1) * n_cl) * 256 + v;
-    const uint8_t* p12 = lut + ((size_t)(iy.t1 * g.tx + ix.t2) * n_cl) * 256 + v;
-    const uint8_t* p21 = lut + ((size_t)(iy.t2 * g.tx + ix.t1) * n_cl) * 256 + v;
-    const uint8_t* p22 = lut + ((size_t)(iy.t2 * g.tx + ix.t2) * n_cl) * 256 + v;
-    for (int c = 0; c < n_cl; c++) {
-      int o = clahe_blend((float)__ldg(p11 + c * 256), (float)__ldg(p12 + c * 256), (float)__ldg(p21 + c * 256),
-                          (float)__ldg(p22 + c * 256), ix, iy);
-      atomicAdd(&s_hist[c * 256 + o], 1u);
+  const float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
+  // the rectangle that surely contains the cell (two pixels of slack: the cell edges are decided by the float32 expression of
+  // interp_coord, every pixel re-derives its cell and the CTA keeps only its own)
+  // cell c covers the coordinates with floor(x / tile - 0.5) == c - 1, i.e. [(c - 0.5) tile, (c + 0.5) tile)
+  const int xa = max(cx * g.tw - (g.tw + 1) / 2 - 2, 0) & ~3, xb = min(cx * g.tw + (g.tw + 1) / 2 + 2, g.W);
+  const int ya0 = max(cy * g.th - (g.th + 1) / 2 - 2, 0), yb0 = min(cy * g.th + (g.th + 1) / 2 + 2, g.H);
+  const int ya = ya0 + band * band_rows, yb = min(ya + band_rows, yb0);
+  const uint8_t* img = src + (size_t)f * g.W * g.H;
+  const int nwords = (xb - xa + 3) >> 2;
+  const bool aligned = ((g.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+  if (xa < xb && ya < yb) {
+    const int total = (yb - ya) * nwords;
+    for (int i = threadIdx.x; i < total; i += SW_THREADS) {
+      const int ry = i / nwords, wx = i - ry * nwords;
+      const int y = ya + ry, x0 = xa + 4 * wx;
+      const float fy = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+      const int ky = (int)floorf(fy);
+      if (ky + 1 != cy) continue;
+      const float ay = __fsub_rn(fy, (float)ky), ay1 = __fsub_rn(1.0f, ay);
+      uint32_t w4;
+      if (aligned && x0 + 3 < g.W) w4 = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * g.W + x0));
+      else {
+        w4 = 0;
+        for (int k = 0; k < 4; k++) if (x0 + k < g.W) w4 |= (uint32_t)img[(size_t)y * g.W + x0 + k] << (8 * k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        if (x >= xb) break;
+        const float fx = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+        const int kx = (int)floorf(fx);
+        if (kx + 1 != cx) continue;
+        const float ax = __fsub_rn(fx, (float)kx), ax1 = __fsub_rn(1.0f, ax);
+        const uint32_t v = (w4 >> (8 * k)) & 255u;
+        const uint32_t* lp = s_lut + v;
+        uint32_t* hp = s_hist;
+#pragma unroll 4
+        for (int c = 0; c < n_cl; c++) {
+          const uint32_t l = lp[c * 256];
+          const float top = __fadd_rn(__fmul_rn((float)(l & 255u), ax1), __fmul_rn((float)((l >> 8) & 255u), ax));
+          const float bot = __fadd_rn(__fmul_rn((float)((l >> 16) & 255u), ax1), __fmul_rn((float)(l >> 24), ax));
+          const float res = __fadd_rn(__fmul_rn(top, ay1), __fmul_rn(bot, ay));
+          const int o = min(max(__float2int_rn(res), 0), 255);   // the blend of four bytes is finite: sat_rint_u8 without its NaN test
+          atomicAdd(hp + c * 256 + o, 1u);
+        }
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_cl * 256; i += 256)
-    if (s_hist[i]) atomicAdd(&out_hist[i], s_hist[i]);
+  uint32_t* oh = out_hist + (size_t)f * n_cl * 256;
+  for (int i = threadIdx.x; i < n_cl * 256; i += SW_THREADS)
+    if (s_hist[i]) atomicAdd(&oh[i], s_hist[i]);
+}
+
+// n planes x n_grids square grids x n_clips clip limits -> entropies [n][n_grids][n_clips] (host pointer)
+int clahe_entropy_sweep_batch_dev(uwip_ctx* ctx, const uint8_t* d_planes, int n, int w, int h, const int* grids, int n_grids,
+                                  const double* clips, int n_clips, int flavour, float* entropies_host) {
+  UWIP_REQUIRE(ctx, n >= 1 && w >= 1 && h >= 1, "bad size");
+  UWIP_REQUIRE(ctx, n_clips >= 1 && n_clips <= SW_MAX_CL, "1..64 clip limits per sweep");
+  UWIP_REQUIRE(ctx, n_grids >= 1 && n_grids <= 16, "1..16 grids per sweep");
+  size_t max_tiles = 0;
+  for (int gi = 0; gi < n_grids; gi++) {
+    UWIP_REQUIRE(ctx, grids[gi] >= 1 && grids[gi] <= 256, "tile grid out of range");
+    TileGeom g = make_geom(w, h, grids[gi], grids[gi]);
+    UWIP_REQUIRE(ctx, (g.EW == w || 2 * w - 2 >= g.EW - 1) && (g.EH == h || 2 * h - 2 >= g.EH - 1), "image too small for grid");
+    max_tiles = std::max(max_tiles, (size_t)grids[gi] * grids[gi]);
+  }
+  uint32_t* d_th = (uint32_t*)uwip_slot(ctx, SLOT_TILEHIST, (size_t)n * max_tiles * 256 * 4);
+  uint8_t* d_tl = (uint8_t*)uwip_slot(ctx, SLOT_TILELUT, (size_t)n * max_tiles * 256 * n_clips + 16);
+  const size_t hist_bytes = (size_t)n * n_grids * n_clips * 256 * 4, ent_bytes = (size_t)n * n_grids * n_clips * 4;
+  char* d_sw = (char*)uwip_slot(ctx, SLOT_SWEEP, 4096 + hist_bytes + ent_bytes);
+  if (!d_th || !d_tl || !d_sw) return UWIP_ERR_NOMEM;
+  int* d_cl_all = (int*)d_sw;   // [n_grids][n_clips] clip limits in counts
+  uint32_t* d_oh = (uint32_t*)(d_sw + 4096);
+  float* d_ent = (float*)(d_sw + 4096 + hist_bytes);
+  std::vector<int> cls((size_t)n_grids * n_clips);
+  for (int gi = 0; gi < n_grids; gi++) {
+    TileGeom g = make_geom(w, h, grids[gi], grids[gi]);
+    for (int i = 0; i < n_clips; i++) cls[(size_t)gi * n_clips + i] = clip_count(clips[i], g.tw * g.th);
+  }
+  UWIP_CUDA(ctx, cudaMemcpyAsync(d_cl_all, cls.data(), sizeof(int) * cls.size(), cudaMemcpyHostToDevice, ctx->stream));
+  UWIP_CUDA(ctx, cudaMemsetAsync(d_oh, 0, hist_bytes, ctx->stream));
+  const size_t smem = (size_t)n_clips * 256 * 8;
+  UWIP_CUDA(ctx, uwip_func_smem(ctx, FUNC_SWEEP, sweep_cell_kernel, smem));
+  for (int gi = 0; gi < n_grids; gi++) {
+    const int tiles = grids[gi];
+    TileGeom g = make_geom(w, h, tiles, tiles);
+    const size_t ntile = (size_t)tiles * tiles;
+    const int* d_cl = d_cl_all + (size_t)gi * n_clips;
+    UWIP_CUDA(ctx, cudaMemsetAsync(d_th, 0, (size_t)n * ntile * 256 * 4, ctx->stream));
+    int splits = pick_splits(ctx, g, n);
+    dim3 grid1(tiles * tiles, splits, n);
+    UWIP_LAUNCH(ctx, "clahe_tilehist", tilehist_kernel<false>, grid1, TH_THREADS, 0, d_planes, g, splits, (const uint8_t*)nullptr, 0, d_th);
+    float lut_scale = 255.0f / (float)(g.tw * g.th);
+    UWIP_LAUNCH(ctx, "clahe_lut", clahe_lut_kernel, (unsigned)(ntile * n), 256, 0, d_th, d_cl, n_clips, lut_scale, d_tl);
+    // bands of rows per cell: enough CTAs to fill the machine, at least 8 rows each
+    const int cells = (tiles + 1) * (tiles + 1);
+    const int cell_rows = g.th + 6;
+    int bands = std::max(1, std::min(cdiv(ctx->sm_count * 4, cells * n), cdiv(cell_rows, 8)));
+    const int band_rows = cdiv(cell_rows, bands);
+    bands = cdiv(cell_rows, band_rows);
+    dim3 grid3(cells * bands, 1, n);
+    // device layout of the histograms and entropies: [grid][frame][clip]
+    uint32_t* d_oh_g = d_oh + (size_t)gi * n * n_clips * 256;
+    UWIP_LAUNCH(ctx, "clahe_sweep_hist", sweep_cell_kernel, grid3, SW_THREADS, smem, d_planes, g, band_rows, bands, d_tl, n_clips, d_oh_g);
+  }
+  UWIP_CHECK(k_entropy(ctx, d_oh, n * n_grids * n_clips, w, h, flavour, d_ent));
+  std::vector<float> tmp((size_t)n * n_grids * n_clips);
+  UWIP_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_ent, ent_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // device layout [grid][frame][clip] -> caller layout [frame][grid][clip]
+  for (int f = 0; f < n; f++)
+    for (int gi = 0; gi < n_grids; gi++)
+      memcpy(entropies_host + ((size_t)f * n_grids + gi) * n_clips, tmp.data() + ((size_t)gi * n + f) * n_clips, sizeof(float) * n_clips);
+  return UWIP_OK;
 }
 
 int clahe_entropy_sweep_dev(uwip_ctx* ctx, const uint8_t* d_plane, int w, int h, int tiles, const double* clips, int n_clips,
                             int flavour, float* entropies_host) {
-  UWIP_REQUIRE(ctx, n_clips >= 1 && n_clips <= SW_MAX_CL, "1..64 clip limits per sweep");
-  UWIP_REQUIRE(ctx, tiles >= 1 && tiles <= 256, "tile grid out of range");
-  TileGeom g = make_geom(w, h, tiles, tiles);
-  UWIP_REQUIRE(ctx, (g.EW == w || 2 * w - 2 >= g.EW - 1) && (g.EH == h || 2 * h - 2 >= g.EH - 1), "image too small for grid");
-  size_t ntile = (size_t)tiles * tiles;
-  uint32_t* d_th = (uint32_t*)uwip_slot(ctx, SLOT_TILEHIST, ntile * 256 * 4);
-  uint8_t* d_tl = (uint8_t*)uwip_slot(ctx, SLOT_TILELUT, ntile * 256 * n_clips + 16);
-  char* d_sw = (char*)uwip_slot(ctx, SLOT_SWEEP, 1024 + (size_t)n_clips * 256 * 4 + (size_t)n_clips * 4);
-  if (!d_th || !d_tl || !d_sw) return UWIP_ERR_NOMEM;
-  int* d_cl = (int*)d_sw;
-  uint32_t* d_oh = (uint32_t*)(d_sw + 1024);
-  float* d_ent = (float*)(d_sw + 1024 + (size_t)n_clips * 256 * 4);
-  int cls[SW_MAX_CL];
-  for (int i = 0; i < n_clips; i++) cls[i] = clip_count(clips[i], g.tw * g.th);
-  UWIP_CUDA(ctx, cudaMemcpyAsync(d_cl, cls, sizeof(int) * n_clips, cudaMemcpyHostToDevice, ctx->stream));
-  UWIP_CUDA(ctx, cudaMemsetAsync(d_th, 0, ntile * 256 * 4, ctx->stream));
-  UWIP_CUDA(ctx, cudaMemsetAsync(d_oh, 0, (size_t)n_clips * 256 * 4, ctx->stream));
-  int splits = pick_splits(ctx, g, 1);
-  dim3 grid1(tiles * tiles, splits, 1);
-  UWIP_LAUNCH(ctx, "clahe_tilehist", tilehist_kernel<false>, grid1, TH_THREADS, 0, d_plane, g, splits, (const uint8_t*)nullptr, 0, d_th);
-  float lut_scale = 255.0f / (float)(g.tw * g.th);
-  UWIP_LAUNCH(ctx, "clahe_lut", clahe_lut_kernel, (unsigned)ntile, 256, 0, d_th, d_cl, n_clips, lut_scale, d_tl);
-  int rows_per = 4;
-  size_t smem = (size_t)n_clips * 256 * 4;
-  UWIP_CUDA(ctx, cudaFuncSetAttribute(sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  UWIP_LAUNCH(ctx, "clahe_sweep_hist", sweep_hist_kernel, cdiv(h, rows_per), 256, smem, d_plane, g, rows_per, d_tl, n_clips, d_oh);
-  UWIP_CHECK(k_entropy(ctx, d_oh, n_clips, w, h, flavour, d_ent));
-  UWIP_CUDA(ctx, cudaMemcpyAsync(entropies_host, d_ent, sizeof(float) * n_clips, cudaMemcpyDeviceToHost, ctx->stream));
-  UWIP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return UWIP_OK;
+  return clahe_entropy_sweep_batch_dev(ctx, d_plane, 1, w, h, &tiles, 1, clips, n_clips, flavour, entropies_host);
 }

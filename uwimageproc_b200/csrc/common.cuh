@@ -36,7 +36,22 @@ struct uwip_ctx {
   void* pinned = nullptr;  // small pinned scratch for scalar results
   size_t pinned_bytes = 0;
   int flags_n = 0;         // frames covered by SLOT_FLAGS (last batched chain / dehaze call)
+  // opt-in dynamic shared memory already granted on THIS context's device, per kernel (cudaFuncSetAttribute is
+  // per device: a process-global flag would leave the second device of a process without the opt-in)
+  static const int kFuncs = 16;
+  size_t func_smem[kFuncs] = {};
 };
+
+enum FuncId { FUNC_GF1A = 0, FUNC_GF1B, FUNC_GF2A, FUNC_GF2B, FUNC_WINDOW, FUNC_WINDOW15, FUNC_SWEEP, FUNC_SWEEP_BATCH, FUNC_GFQ };
+
+// grant `bytes` of dynamic shared memory to `kern` on the context's device (once per context and size)
+template <class K>
+static inline cudaError_t uwip_func_smem(uwip_ctx* ctx, int id, K kern, size_t bytes) {
+  if (bytes <= ctx->func_smem[id]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) ctx->func_smem[id] = bytes;
+  return e;
+}
 
 enum Slot {
   SLOT_STAGE_IN = 0,  // host-API staging: input frames
@@ -352,6 +367,7 @@ int histretch_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, in
 int clahe_planes_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty);
 int aclahe_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, double clip, int tx, int ty, int hsv_round, const uint8_t* d_prelut /*optional per-frame stretch LUT fused in front*/, FrameState* fs_minmax /*optional: accumulate dehaze D0 min/max of the output*/);
 int clahe_entropy_sweep_dev(uwip_ctx* ctx, const uint8_t* d_plane, int w, int h, int tiles, const double* clips, int n_clips, int flavour, float* entropies_host);
+int clahe_entropy_sweep_batch_dev(uwip_ctx* ctx, const uint8_t* d_planes, int n, int w, int h, const int* grids, int n_grids, const double* clips, int n_clips, int flavour, float* entropies_host);
 
 // dehaze.cu
 struct DehazeDebug {  // optional float64 stage outputs for the stage-wise host API (device pointers)
@@ -365,6 +381,8 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
 int frame_state_reset(uwip_ctx* ctx, FrameState* fs, int n);
 int dehaze_wave_frames(const uwip_ctx* ctx, int w);  // frames whose guided-filter strips fill the SMs exactly once
 FrameState* frame_state_get(uwip_ctx* ctx, int n);
+int boxfilter_f64_dev(uwip_ctx* ctx, const double* d_src, double* d_tmp, double* d_dst, int w, int h, int r);
+int guided_filter_u8_dev(uwip_ctx* ctx, const uint8_t* d_guide, const double* d_p, double* d_q, int w, int h, int range, int r, double eps, FrameState* fs);
 
 // synth.cu
 int synth_frames_dev(uwip_ctx* ctx, uint8_t* d_dst, uint32_t seed, int first, int n, int w, int h);

@@ -724,913 +724,21 @@ __device__ __forceinline__ int coef_chunk(int gq, int c, int j) {  // physical c
   return c ^ ((gq >> 1) & 3);
 }
 
-// V-phase of the coefficient readers (GF1b, GF2b): the entering and the leaving row were brought to shared
-// memory by one TMA bulk copy each ([2][NT quads][NP chunks]); every value goes through fp64.
-__device__ __forceinline__ float4 lds128(unsigned addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-template <int NP, int NT, bool ENTER, bool LEAVE, bool FULL>
-__device__ __forceinline__ void gf_accum_staged_case(const float4* __restrict__ stg, int gq, unsigned cmask, double (&Vd)[4][NP]) {
-  // quad blocks are NP*16 bytes and block-aligned, so (logical chunk ^ swizzle) * 16 is the block address
-  // with the swizzle folded in, XOR a compile-time constant: one LOP3 per load
-  const unsigned swz = (unsigned)coef_chunk<NP>(gq, 0, 0) << 4;
-  const unsigned be = (unsigned)__cvta_generic_to_shared(stg + (size_t)threadIdx.x * NP) + swz;
-  const unsigned bl = (unsigned)__cvta_generic_to_shared(stg + (size_t)(NT + threadIdx.x) * NP) + swz;
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-#pragma unroll
-    for (int j = 0; j < NP / 4; j++) {
-      const unsigned q16 = (unsigned)(NP == 8 ? 2 * c + j : c) << 4;
-      float4 e, l;
-      if (ENTER) e = lds128(be ^ q16);
-      if (LEAVE) l = lds128(bl ^ q16);
-      if (FULL || (cmask & (1u << c))) {
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-          if (ENTER && LEAVE) Vd[c][4 * j + m] += (double)quad_get(e, m) - (double)quad_get(l, m);
-          else if (ENTER) Vd[c][4 * j + m] += (double)quad_get(e, m);
-          else Vd[c][4 * j + m] -= (double)quad_get(l, m);
-        }
-      }
-    }
-  }
-}
-// uniform dispatch: steady state (both rows, all four columns inside the image) is the straight-line case
-template <int NP, int NT>
-__device__ __forceinline__ void gf_accum_staged(const float4* __restrict__ stg, int gq, bool enter, bool leave, unsigned cmask, double (&Vd)[4][NP]) {
-  if (enter && leave) {
-    if (cmask == 0xfu) gf_accum_staged_case<NP, NT, true, true, true>(stg, gq, cmask, Vd);
-    else gf_accum_staged_case<NP, NT, true, true, false>(stg, gq, cmask, Vd);
-  } else if (enter) {
-    gf_accum_staged_case<NP, NT, true, false, false>(stg, gq, cmask, Vd);
-  } else if (leave) {
-    gf_accum_staged_case<NP, NT, false, true, false>(stg, gq, cmask, Vd);
-  }
-}
-
 // -------------------------------------------------------------------------------------------------
-// policies: what is accumulated per pixel (accum), and what is made of the window sums (column)
+// the guided-filter marches: warp-specialised pipeline (gfpipe.cuh)
 // -------------------------------------------------------------------------------------------------
-constexpr int GF_NSEG = 8;    // scan segments per quad-total row
-constexpr int GF_SEGQ = 28;   // quads per segment (7 x 16 bytes: an odd chunk count keeps the vector loads conflict-free)
-constexpr int GF_GP = GF_NSEG * GF_SEGQ;  // pitch of a quad-total row = max threads per CTA
-
-// GF1a: guide = normI (k units), p = max(t_blue, tmin) and max(t_green, tmin)
-struct PolGF1a {
-  static constexpr int NI = 9, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = false;
-  static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
-  static constexpr bool EARLY_SCAN = false, UNCOND_STAGE = true;
-  struct Shared {
-    double pT[2][256];  // p_c as a function of the window-min k'
-    FrameConst fc;
-    double epsN_k;      // eps * range^2 (read at its use: a register held across the march ends up in a spill slot)
-  };
-  struct Raw { uint4 k; uint32_t m; };
-  GfCommon g; Shared* sh; int Wp, H, f;
-  const uint32_t* kq; const uint8_t* mg; float* ab;
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
-    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
-    size_t n_pp = (size_t)Wp * H;
-    kq = g.kq + (size_t)f * n_pp;
-    mg = g.mg + (size_t)f * n_pp;
-    ab = g.ab + (size_t)f * 8 * n_pp;
-    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
-    __syncthreads();
-    double range = (double)sh->fc.range;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-      int c = i >> 8, k = i & 255;
-      double t = 1.0 - ((double)k / range) / sh->fc.Bt[c];     // transmission_map (BGDehaze.py:35-36)
-      sh->pT[c][k] = grid_round<28>((t < g.tmin) ? g.tmin : t);  // np.maximum(t, tmin) (NaN stays NaN), on the 2^-28 grid
-    }
-    if (threadIdx.x == 0) sh->epsN_k = g.eps * range * range;
-    __syncthreads();
-  }
-  // staging slot s (0..3 = 2 buffers x enter/leave) of this thread: one uint4 + one u32
-  static constexpr int STAGE_BYTES = 4 * NT * 20;
-  __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx) const {
-    size_t o = (size_t)y * Wp + gx;
-    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 16, kq + o);
-    cp_async4(st + (size_t)4 * NT * 16 + ((size_t)s * NT + threadIdx.x) * 4, mg + o);
-  }
-  __device__ __forceinline__ void stage_read(const unsigned char* st, int s, Raw& r) const {
-    r.k = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 16);
-    r.m = *reinterpret_cast<const uint32_t*>(st + (size_t)4 * NT * 16 + ((size_t)s * NT + threadIdx.x) * 4);
-  }
-  template <int SIGN, bool FULL>
-  __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI > 0 ? NI : 1], double (&Vd)[4][ND]) const {
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      uint32_t w = quad_get(r.k, c);
-      uint32_t kb = w & 255u, kg = (w >> 8) & 255u, kr = (w >> 16) & 255u, mb = w >> 24, mgv = (r.m >> (8 * c)) & 255u;
-      if (SIGN > 0) {
-        Vi[c][0] += kb; Vi[c][1] += kg; Vi[c][2] += kr;
-        Vi[c][3] += kb * kb; Vi[c][4] += kb * kg; Vi[c][5] += kb * kr;
-        Vi[c][6] += kg * kg; Vi[c][7] += kg * kr; Vi[c][8] += kr * kr;
-      } else {
-        Vi[c][0] -= kb; Vi[c][1] -= kg; Vi[c][2] -= kr;
-        Vi[c][3] -= kb * kb; Vi[c][4] -= kb * kg; Vi[c][5] -= kb * kr;
-        Vi[c][6] -= kg * kg; Vi[c][7] -= kg * kr; Vi[c][8] -= kr * kr;
-      }
-      if (FULL || (cmask & (1u << c))) {
-        double pb = sh->pT[0][mb], pg = sh->pT[1][mgv];
-        if (SIGN < 0) { pb = -pb; pg = -pg; }
-        double db = u2d(kb), dg = u2d(kg), dr = u2d(kr);
-        Vd[c][0] += pb;
-        Vd[c][1] += pg;
-        Vd[c][2] = fma(db, pb, Vd[c][2]); Vd[c][3] = fma(dg, pb, Vd[c][3]); Vd[c][4] = fma(dr, pb, Vd[c][4]);
-        Vd[c][5] = fma(db, pg, Vd[c][5]); Vd[c][6] = fma(dg, pg, Vd[c][6]); Vd[c][7] = fma(dr, pg, Vd[c][7]);
-      }
-    }
-  }
-  __device__ __forceinline__ void row_begin(int, int) {}
-  // results go out pixel by pixel: two 16-byte chunks (one per filter) into the swizzled quad block
-  __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
-    double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
-    double M[6], Sd[3], A[6], rdet;
-    gf_build_M(si, N, *(volatile double*)&sh->epsN_k * N * N, M, Sd);
-    gf_adjugate(M, A, rdet);
-    double a[3], b;
-    const int gq = x >> 2, c = x & 3;
-    float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 8;
-    gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 2, a, b);
-    blk[coef_chunk<8>(gq, c, 0)] = coef_pack(a, b);
-    gf_solve(A, rdet, Sd, N, invN, sd[1], sd + 5, a, b);
-    blk[coef_chunk<8>(gq, c, 1)] = coef_pack(a, b);
-  }
-  __device__ __forceinline__ void store_pair(int, int) {}
-  __device__ void finish() {}
-};
-
-// GF1b: q = (box(a).k + box(b))/N for blue and green -> J (dehazed_BG) + reductions
-struct PolGF1b {
-  static constexpr int NI = 0, ND = 8, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
-  static constexpr bool EARLY_SCAN = true, UNCOND_STAGE = false;
-  static constexpr int EARLY_ROW = 1, ROWST_BYTES = 0;  // row_begin's one 16-byte load goes out before the accumulate phase
-  struct Shared {
-    double nrm[256];
-    FrameConst fc;
-  };
-  struct Raw {};
-  GfCommon g; Shared* sh; int W, Wp, H, f;
-  const uint32_t* kq; const float* ab; float* J;
-  float jmn[2], jmx[2];
-  long long jsum[2];   // sum of bits(J*2^32 + 1.5*2^52): exact 2^-32 fixed point, independent of the partition
-  unsigned cnt, rmn, rmx, rsum, nanf;
-  uint4 krow;
-  float o[2][2];
-  double* dbg;   // stage-wise API only: refined t of frame 0
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
-    g = gc; sh = s; W = gg.W; Wp = gg.Wp; H = gg.H; f = frame;
-    dbg = (frame == 0) ? gc.dbg_tref : nullptr;
-    size_t n_pp = (size_t)Wp * H;
-    kq = g.kq + (size_t)f * n_pp;
-    ab = g.ab + (size_t)f * 8 * n_pp;
-    J = g.J + (size_t)f * 2 * n_pp;
-    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->nrm[i] = (double)i / (double)sh->fc.range;
-    jmn[0] = jmn[1] = __int_as_float(0x7f800000); jmx[0] = jmx[1] = -__int_as_float(0x7f800000);
-    jsum[0] = jsum[1] = 0;
-    cnt = 0; rmn = 255; rmx = 0; rsum = 0; nanf = 0;
-    __syncthreads();
-  }
-  static constexpr int NP = 8, STAGE_BYTES = 2 * NP * NT * 16;
-  __device__ __forceinline__ const float* coef_rows() const { return ab; }
-  __device__ __forceinline__ void row_begin(int y, int gx) { krow = __ldg(reinterpret_cast<const uint4*>(kq + (size_t)y * Wp + gx)); }
-  __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd) {
-    double invN = rcp_fast(u2d((uint32_t)Ncnt));
-    uint32_t w = quad_get(krow, x & 3);
-    uint32_t k[3] = {w & 255u, (w >> 8) & 255u, (w >> 16) & 255u};
-    double kd[3] = {u2d(k[0]), u2d(k[1]), u2d(k[2])};
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const double* s = sd + 4 * c;
-      double q = (s[0] * kd[0] + s[1] * kd[1] + s[2] * kd[2] + s[3]) * invN;   // guidedfilter.py:100-101
-      if (dbg) dbg[(size_t)c * W * H + (size_t)y * W + x] = q;
-      double Bc = sh->fc.B[c];
-      double Jv = (sh->nrm[k[c]] - Bc) * rcp_fast(q) + Bc;                    // BGDehaze.py:53,55
-      float Jf = (float)Jv;
-      o[cc][c] = Jf;
-      if (!(fabsf(Jf) < 262144.0f)) { nanf |= 1u; Jf = 0.f; }
-      jmn[c] = fminf(jmn[c], Jf);
-      jmx[c] = fmaxf(jmx[c], Jf);
-      jsum[c] += __double_as_longlong(fma((double)Jf, 4294967296.0, 6755399441055744.0));
-    }
-    cnt++;
-    rmn = min(rmn, k[2]); rmx = max(rmx, k[2]); rsum += k[2];
-  }
-  __device__ __forceinline__ void store_pair(int y, int x) {
-    size_t n_pp = (size_t)Wp * H, pp = (size_t)y * Wp + x;
-    *reinterpret_cast<float2*>(J + pp) = make_float2(o[0][0], o[1][0]);
-    *reinterpret_cast<float2*>(J + n_pp + pp) = make_float2(o[0][1], o[1][1]);
-  }
-  __device__ void finish() {
-    FrameState& s = g.fs[f];
-    for (int c = 0; c < 2; c++) {
-      float a = warp_min_f32(jmn[c]), b = warp_max_f32(jmx[c]);
-      long long sm = warp_sum_i64(jsum[c] - (long long)cnt * __double_as_longlong(6755399441055744.0));
-      if ((threadIdx.x & 31) == 0) {
-        if (a <= b) {
-          atomicMin(&s.jmin_key[c], dkey((double)a));
-          atomicMax(&s.jmax_key[c], dkey((double)b));
-        }
-        atomicAdd((unsigned long long*)&s.jsum_fix[c], (unsigned long long)sm);
-      }
-    }
-    unsigned a = warp_reduce_min_u32(rmn), b = warp_reduce_max_u32(rmx);
-    unsigned rs = __reduce_add_sync(0xffffffffu, rsum);
-    unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&s.rmin, a);
-      atomicMax(&s.rmax, b);
-      atomicAdd(&s.rsum, (unsigned long long)rs);
-      if (nf) atomicOr(&s.nan_flag, nf);
-    }
-  }
-};
-
-// GF2a: guide = normYiCrCb (k units), p = S (BGDehaze.py:83)
-struct PolGF2a {
-  static constexpr int NI = 9, ND = 4, MINB = 1, MAXREG = 255, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = true, INT_HALF = false, DBUF = true, META = true, DELAY = true;
-  static constexpr int EARLY_ROW = 0, ROWST_BYTES = 0;
-  static constexpr bool EARLY_SCAN = false, UNCOND_STAGE = false;
-  struct Shared { FrameConst fc; };
-  struct Raw { uint4 y; float4 s; };
-  GfCommon g; Shared* sh; int Wp, H, f;
-  const uint32_t* ycc; const float* sp; float* ab;
-  uint32_t ysub;   // (yi_min, yi_min, yi_min, yj_min): no byte can borrow
-  double epsN_k; unsigned nanf;
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
-    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
-    size_t n_pp = (size_t)Wp * H;
-    ycc = g.ycc + (size_t)f * n_pp;
-    sp = g.splane + (size_t)f * n_pp;
-    ab = g.ab + (size_t)f * 8 * n_pp;
-    if (threadIdx.x == 0) load_frame_const(g.fs[f], sh->fc);
-    __syncthreads();
-    double rng = (double)sh->fc.yi_rng;
-    epsN_k = g.eps * rng * rng;
-    uint32_t a = (uint32_t)sh->fc.yi_min, b = (uint32_t)sh->fc.yj_min;
-    ysub = a | (a << 8) | (a << 16) | (b << 24);
-    nanf = 0;
-  }
-  // staging slot s of this thread: the packed guide quad and the S quad
-  static constexpr int STAGE_BYTES = 4 * NT * 32;
-  __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx) const {
-    size_t o = (size_t)y * Wp + gx;
-    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 32, ycc + o);
-    cp_async16(st + ((size_t)s * NT + threadIdx.x) * 32 + 16, sp + o);
-  }
-  __device__ __forceinline__ void stage_read(const unsigned char* st, int s, Raw& r) const {
-    r.y = *reinterpret_cast<const uint4*>(st + ((size_t)s * NT + threadIdx.x) * 32);
-    r.s = *reinterpret_cast<const float4*>(st + ((size_t)s * NT + threadIdx.x) * 32 + 16);
-  }
-  template <int SIGN, bool FULL>
-  __device__ __forceinline__ void accum(const Raw& r, unsigned cmask, uint32_t (&Vi)[4][NI], double (&Vd)[4][ND]) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      if (FULL || (cmask & (1u << c))) {
-        uint32_t w = quad_get(r.y, c) - ysub;
-        uint32_t g0 = w & 255u, g1 = (w >> 8) & 255u, g2 = (w >> 16) & 255u;
-        double S = (double)quad_get(r.s, c);
-        if (SIGN > 0) {
-          if (!(S == S)) nanf = 1u;
-          Vi[c][0] += g0; Vi[c][1] += g1; Vi[c][2] += g2;
-          Vi[c][3] += g0 * g0; Vi[c][4] += g0 * g1; Vi[c][5] += g0 * g2;
-          Vi[c][6] += g1 * g1; Vi[c][7] += g1 * g2; Vi[c][8] += g2 * g2;
-        } else {
-          S = -S;
-          Vi[c][0] -= g0; Vi[c][1] -= g1; Vi[c][2] -= g2;
-          Vi[c][3] -= g0 * g0; Vi[c][4] -= g0 * g1; Vi[c][5] -= g0 * g2;
-          Vi[c][6] -= g1 * g1; Vi[c][7] -= g1 * g2; Vi[c][8] -= g2 * g2;
-        }
-        Vd[c][0] += S;
-        Vd[c][1] = fma(u2d(g0), S, Vd[c][1]); Vd[c][2] = fma(u2d(g1), S, Vd[c][2]); Vd[c][3] = fma(u2d(g2), S, Vd[c][3]);
-      }
-    }
-  }
-  __device__ __forceinline__ void row_begin(int, int) {}
-  __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd) {
-    double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
-    double M[6], Sd[3], A[6], rdet, a[3], b;
-    gf_build_M(si, N, epsN_k * N * N, M, Sd);
-    gf_adjugate(M, A, rdet);
-    gf_solve(A, rdet, Sd, N, invN, sd[0], sd + 1, a, b);
-    const int gq = x >> 2;
-    float4* blk = reinterpret_cast<float4*>(ab) + ((size_t)y * (Wp >> 2) + gq) * 4;
-    blk[coef_chunk<4>(gq, x & 3, 0)] = coef_pack(a, b);
-  }
-  __device__ __forceinline__ void store_pair(int, int) {}
-  __device__ void finish() {
-    unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
-    if ((threadIdx.x & 31) == 0 && nf) atomicOr(&g.fs[f].nan_flag, 1u);
-  }
-};
-
-// GF2b: refined S -> exposure product -> min/max (BGDehaze.py:84-89)
-struct PolGF2b {
-  static constexpr int NI = 0, ND = 4, MINB = 2, MAXREG = 128, NT = 224, NAUX = 1;
-  static constexpr bool PREFETCH = false, INT_HALF = false, DBUF = true, META = false, DELAY = false;
-  static constexpr bool EARLY_SCAN = true, UNCOND_STAGE = false;
-  static constexpr int EARLY_ROW = 2, ROWST_BYTES = NT * 64;  // row_begin's four 16-byte loads are staged through shared memory (cp.async)
-  typedef ExpShared Shared;
-  struct Raw {};
-  GfCommon g; Shared* sh; int Wp, H, f;
-  const uint32_t* kq; const uint32_t* ycc; const float* J; const float* ab; float* refS;
-  double omn, omx; unsigned nanf;
-  uint4 krow, yrow; float4 jb, jg;
-  float o[2];
-  __device__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
-    g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
-    size_t n_pp = (size_t)Wp * H;
-    kq = g.kq + (size_t)f * n_pp;
-    ycc = g.ycc + (size_t)f * n_pp;
-    J = g.J + (size_t)f * 2 * n_pp;
-    ab = g.ab + (size_t)f * 8 * n_pp;
-    refS = g.refS + (size_t)f * n_pp;
-    exp_shared_init(sh, g.fs[f], (double)gg.W * (double)gg.H);
-    omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
-  }
-  static constexpr int NP = 4, STAGE_BYTES = 2 * NP * NT * 16;
-  __device__ __forceinline__ const float* coef_rows() const { return ab; }
-  __device__ __forceinline__ void row_begin(int y, int gx) {
-    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
-    krow = __ldg(reinterpret_cast<const uint4*>(kq + o));
-    yrow = __ldg(reinterpret_cast<const uint4*>(ycc + o));
-    jb = __ldg(reinterpret_cast<const float4*>(J + o));
-    jg = __ldg(reinterpret_cast<const float4*>(J + n_pp + o));
-  }
-  // the same four loads as asynchronous copies into this thread's staging slots, and their pick-up
-  __device__ __forceinline__ void row_prefetch(unsigned char* rs, int y, int gx) const {
-    size_t n_pp = (size_t)Wp * H, o = (size_t)y * Wp + gx;
-    uint4* slot = reinterpret_cast<uint4*>(rs) + threadIdx.x;
-    cp_async16(slot, kq + o);
-    cp_async16(slot + NT, ycc + o);
-    cp_async16(slot + 2 * NT, J + o);
-    cp_async16(slot + 3 * NT, J + n_pp + o);
-    cp_async_commit();
-  }
-  __device__ __forceinline__ void row_pickup(const unsigned char* rs) {
-    cp_async_wait_all();
-    const uint4* slot = reinterpret_cast<const uint4*>(rs) + threadIdx.x;
-    krow = slot[0];
-    yrow = slot[NT];
-    uint4 a = slot[2 * NT], b = slot[3 * NT];
-    jb = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-    jg = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
-  }
-  __device__ __forceinline__ void column(int cc, int, int x, int Ncnt, const uint32_t*, const double* sd) {
-    double invN = rcp_fast(u2d((uint32_t)Ncnt));
-    int c4 = x & 3;
-    uint32_t yw = quad_get(yrow, c4);
-    uint32_t ymin = (uint32_t)sh->fc.yi_min;
-    double g0 = u2d((yw & 255u) - ymin), g1 = u2d(((yw >> 8) & 255u) - ymin), g2 = u2d(((yw >> 16) & 255u) - ymin);
-    double q = (sd[0] * g0 + sd[1] * g1 + sd[2] * g2 + sd[3]) * invN;
-    float qf = (float)q;
-    o[cc] = qf;
-    double qr = (double)qf;
-    double rb = norm_j_fast(quad_get(jb, c4), sh->fc, 0), rg = norm_j_fast(quad_get(jg, c4), sh->fc, 1);
-    double rr = sh->rt.redN[(quad_get(krow, c4) >> 16) & 255u];
-    // min / max over the three channels of restored * refinedS
-    double o0 = rb * qr, o1 = rg * qr, o2 = rr * qr;
-    double os = (o0 + o1) + o2;
-    if (!(os == os) || fabs(os) > 1.0e300) { nanf = 1u; }  // any NaN / inf poisons the sum
-    else {  // plain compare-selects: no NaN in here, fmin/fmax would pay for their NaN rules
-      double lo = o0 < o1 ? o0 : o1, hi = o0 < o1 ? o1 : o0;
-      lo = o2 < lo ? o2 : lo; hi = o2 > hi ? o2 : hi;
-      omn = lo < omn ? lo : omn;
-      omx = hi > omx ? hi : omx;
-    }
-  }
-  __device__ __forceinline__ void store_pair(int y, int x) {
-    *reinterpret_cast<float2*>(refS + (size_t)y * Wp + x) = make_float2(o[0], o[1]);
-  }
-  __device__ void finish() {
-    double a = warp_min_f64(omn), b = warp_max_f64(omx);
-    unsigned nf = __reduce_or_sync(0xffffffffu, nanf);
-    if ((threadIdx.x & 31) == 0) {
-      if (a <= b) {
-        atomicMin(&g.fs[f].omin_key, dkey(a));
-        atomicMax(&g.fs[f].omax_key, dkey(b));
-      }
-      if (nf) atomicOr(&g.fs[f].nan_flag, 1u);
-    }
-  }
-};
-
-// -------------------------------------------------------------------------------------------------
-// the quad-march kernel
-// -------------------------------------------------------------------------------------------------
-// One scan task: GF_SEGQ consecutive quad totals of one moment -> inclusive prefix over the whole row.
-// The eight tasks of a moment sit in eight adjacent lanes; their segment totals are exchanged with
-// shuffles.  The segment lives in registers between the load and the store (one pass over shared
-// memory); the in-register prefix is done per group of four to keep the dependent chain short.
-template <class T, class V4>
-__device__ __forceinline__ void gf_scan_task(T* row, int seg, bool live) {
-  constexpr int VW = sizeof(V4) / sizeof(T);  // 4 (u32) or 2 (f64)
-  constexpr int NG = GF_SEGQ / 4;             // groups of four values
-  T* p = row + seg * GF_SEGQ;
-  T v[GF_SEGQ];
-#pragma unroll
-  for (int i = 0; i < GF_SEGQ; i += VW) {
-    V4 q;
-    if (live) q = *reinterpret_cast<const V4*>(p + i);
-    if constexpr (VW == 4) { v[i] = live ? q.x : T(0); v[i + 1] = live ? q.y : T(0); v[i + 2] = live ? q.z : T(0); v[i + 3] = live ? q.w : T(0); }
-    else { v[i] = live ? q.x : T(0); v[i + 1] = live ? q.y : T(0); }
-  }
-  T gt[NG];
-#pragma unroll
-  for (int g = 0; g < NG; g++) {  // prefix inside each group of four (independent chains of three)
-    v[4 * g + 1] += v[4 * g]; v[4 * g + 2] += v[4 * g + 1]; v[4 * g + 3] += v[4 * g + 2];
-    gt[g] = v[4 * g + 3];
-  }
-#pragma unroll
-  for (int g = 1; g < NG; g++) gt[g] += gt[g - 1];  // inclusive prefix of the group totals
-  T incl = gt[NG - 1];
-#pragma unroll
-  for (int d = 1; d < GF_NSEG; d <<= 1) {
-    T o = __shfl_up_sync(0xffffffffu, incl, d, GF_NSEG);
-    if (seg >= d) incl += o;
-  }
-  T run = __shfl_up_sync(0xffffffffu, incl, 1, GF_NSEG);  // exclusive offset of this segment
-  if (seg == 0) run = 0;
-  if (live) {
-#pragma unroll
-    for (int i = 0; i < GF_SEGQ; i += VW) {
-      T off = run + (i >= 4 ? gt[i / 4 - 1] : T(0));
-      V4 q;
-      if constexpr (VW == 4) { q.x = v[i] + off; q.y = v[i + 1] + off; q.z = v[i + 2] + off; q.w = v[i + 3] + off; }
-      else { q.x = v[i] + off; q.y = v[i + 1] + off; }
-      *reinterpret_cast<V4*>(p + i) = q;
-    }
-  }
-}
-
-// shared-memory layout of one published row; every pitch is a compile-time constant so that each
-// access is base register + immediate:
-//   Pd01 [ND][NT] double2 (prefix 0,1 of the quad) | Pd2 [ND][NT] f64 (prefix 2; prefix 3 = the quad total
-//   is the difference of two neighbouring entries of the scanned totals and is not stored)
-//   Gd [ND][GF_GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GF_GP] u32 | policy tables | row staging | mbarrier
-template <class P>
-struct GfSmem {
-  static constexpr int NT = P::NT, NI = P::NI, ND = P::ND;
-  static constexpr size_t off_d23 = (size_t)ND * NT * 16;
-  static constexpr size_t off_gd = off_d23 + (size_t)ND * NT * 8;
-  static constexpr size_t off_pi = off_gd + (size_t)ND * GF_GP * 8;
-  static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
-  static constexpr size_t buf_bytes = (off_gi + (size_t)NI * GF_GP * 4 + 127) & ~(size_t)127;  // one published row
-  // DBUF: two copies addressed by the parity of the output row - the next row can be published while slow
-  // warps still read this one, which removes the third CTA barrier of a row
-  static constexpr size_t off_sh = buf_bytes * (P::DBUF ? 2 : 1);
-  static constexpr size_t off_st = (off_sh + sizeof(typename P::Shared) + 127) & ~(size_t)127;  // quad blocks stay block-aligned
-  static constexpr size_t off_bar = off_st + P::STAGE_BYTES;
-  static constexpr size_t off_row = off_bar + 16;          // per-thread staging of row_begin's inputs (EARLY_ROW == 2)
-  static constexpr size_t bytes = off_row + P::ROWST_BYTES;
-};
-
-// Thread roles: threads 0..NT-1 are WORKERS (one quad of the strip each); the last warp is the AUXILIARY
-// warp: it turns the quad totals of the published row into prefixes while the workers already add the
-// next row to their running sums, and (plane readers) its lane 0 is the TMA producer of the row staging.
-//
-// One output row:   workers publish(yo) | bar A | aux scan(yo) || workers acc(row yin+1) | bar B |
-//                   aux TMA(row yin+2) || workers window sums + per-pixel work of yo | bar C
-template <class P>
-__global__ void __launch_bounds__(P::NT + 32 * P::NAUX) __maxnreg__(P::MAXREG) gf_march_kernel(GfCommon gc, GfGeom gg) {
-  constexpr int NI = P::NI, ND = P::ND, NT = P::NT, GP = GF_GP;
-  constexpr int NIa = NI > 0 ? NI : 1;
-  typedef GfSmem<P> L;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* Pd01 = reinterpret_cast<double2*>(smem_raw);
-  double* Pd2 = reinterpret_cast<double*>(smem_raw + L::off_d23);
-  double* Gd = reinterpret_cast<double*>(smem_raw + L::off_gd);
-  uint4* Pi = reinterpret_cast<uint4*>(smem_raw + L::off_pi);
-  uint32_t* Gi = reinterpret_cast<uint32_t*>(smem_raw + L::off_gi);
-  auto select_buffer = [&](int yo) {  // published-row arrays of output row yo
-    unsigned char* b = smem_raw + ((P::DBUF && (yo & 1)) ? L::buf_bytes : 0);
-    Pd01 = reinterpret_cast<double2*>(b);
-    Pd2 = reinterpret_cast<double*>(b + L::off_d23);
-    Gd = reinterpret_cast<double*>(b + L::off_gd);
-    Pi = reinterpret_cast<uint4*>(b + L::off_pi);
-    Gi = reinterpret_cast<uint32_t*>(b + L::off_gi);
-  };
-  typename P::Shared* sh = reinterpret_cast<typename P::Shared*>(smem_raw + L::off_sh);
-  unsigned char* stage = smem_raw + L::off_st;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
-  P pol;
-  pol.init(gc, blockIdx.z, sh, gg);
-
-  const int t = threadIdx.x;
-  const bool aux = t >= NT;
-  const int lane = t & 31;
-  const int NQ = gg.NQ;
-  const int W = gg.W, H = gg.H, r = gg.r;
-  const int xs = blockIdx.x * gg.SW;
-  const int gx = xs - gg.HL - 4 + 4 * t;      // image column of this thread's quad (multiple of 4)
-  const bool qact = t < NQ;
-  unsigned cmask = 0;                         // columns of the quad that are image columns; quad 0 is the zero guard
-  if (qact && t > 0) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) if (gx + c >= 0 && gx + c < W) cmask |= 1u << c;
-  }
-  const bool qload = cmask != 0;              // then 0 <= gx < Wp: the whole quad is readable
-  const int ys = blockIdx.y * gg.seg_h, ye = min(ys + gg.seg_h, H);
-  const int y_first = max(ys - r, 0);         // first row that enters the running sums
-  const int y_begin = ys - r, y_end = ye + r; // rows yin of the march
-  // output quads of this strip
-  const int tq0 = gg.HL / 4 + 1;
-  const bool oact = (t >= tq0) && (t < tq0 + gg.SW / 4) && (gx < W);
-  // Everything the march loop needs to know about this thread's quad lives in ONE word (at 255 registers the compiler
-  // otherwise parks the individual flags and counts in local-memory spill slots and reloads them every row):
-  //   bits 28..31 cmask; bits 7c..7c+6 the horizontal pixel count of the window of column c, set for output quads only
-  //   (so "output quad" == low 7 bits non-zero).  Counts need 2r + 1 <= 127; wider windows recompute them per row.
-  const bool nx_packed = (2 * gg.r + 1) <= 127;
-  unsigned meta = cmask << 28;
-  if (oact) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      int x = gx + c;
-      int nx = (x < gg.W) ? min(x + gg.r, gg.W - 1) - max(x - gg.r, 0) + 1 : 0;
-      meta |= (unsigned)(nx_packed ? nx : 1) << (7 * c);
-    }
-  }
-  const int rho = r >> 2;
-  // addresses used by the window sums: the quads at -rho / +rho and the totals around them
-  const int tlo_h = oact ? t - rho : 0, thi_h = oact ? t + rho : 0;  // policies without META keep them across the march
-  // quads of this strip that lie inside the padded image: [tA, tB) (the guard quad 0 stays zero)
-  const int tA = max(1, (gg.HL + 4 - xs) >> 2), tB = min(NQ, (gg.Wp - xs + gg.HL + 4) >> 2);
-
-  // the quad-total rows are scanned over their whole length: keep the unused tail finite
-  for (int bsel = 0; bsel < (P::DBUF ? 2 : 1); bsel++) {
-    select_buffer(bsel);
-    for (int i = t; i < GP; i += NT + 32 * P::NAUX) {
-#pragma unroll
-      for (int k = 0; k < NI; k++) Gi[k * GP + i] = 0u;
-#pragma unroll
-      for (int k = 0; k < ND; k++) Gd[k * GP + i] = 0.0;
-    }
-  }
-  if constexpr (!P::PREFETCH) {
-    if (t == NT) mbar_init(mbar, 1);
-  }
-  __syncthreads();
-
-  uint32_t Vi[4][NIa];
-  double Vd[4][ND];
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-#pragma unroll
-    for (int k = 0; k < NIa; k++) Vi[c][k] = 0;
-#pragma unroll
-    for (int k = 0; k < ND; k++) Vd[c][k] = 0.0;
-  }
-
-  // TMA producer of the plane readers (aux lane 0): the entering and the leaving row of every plane for
-  // march row `yi` land in the staging buffer and complete one mbarrier phase
-  auto tma_rows = [&](int yi) {
-    if constexpr (!P::PREFETCH) {
-      if (yi >= y_end) return;
-      const int yli = yi - 2 * r - 1;
-      const bool en = (yi >= 0 && yi < H), le = (yli >= y_first);
-      // one bulk copy per row: (tB - tA) quads x NP chunks of 16 bytes, contiguous in the interleaved layout
-      const unsigned row_bytes = (unsigned)(tB - tA) * 16u * P::NP;
-      mbar_arrive_expect_tx(mbar, ((en ? 1u : 0u) + (le ? 1u : 0u)) * row_bytes);
-      float4* stg = reinterpret_cast<float4*>(stage);
-      const int gqa = (xs - gg.HL - 4 + 4 * tA) >> 2;   // global quad index of strip quad tA
-      const float4* rows = reinterpret_cast<const float4*>(pol.coef_rows());
-      const size_t qpr = (size_t)(gg.Wp >> 2);
-      if (en) tma_bulk_g2s(stg + (size_t)tA * P::NP, rows + ((size_t)yi * qpr + gqa) * P::NP, row_bytes, mbar);
-      if (le) tma_bulk_g2s(stg + (size_t)(NT + tA) * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, mbar);
-    }
-  };
-  // workers: add march row yi to the running sums and drop row yi - 2r - 1
-  auto acc = [&](int yi) {
-    if (yi >= y_end) return;
-    const int yli = yi - 2 * r - 1;
-    const bool enter = (yi >= 0 && yi < H), leave = (yli >= y_first);
-    const int par = (yi - y_begin) & 1;
-    if constexpr (P::PREFETCH) {
-      // this row was requested one march row ago (cp.async, no registers held meanwhile); the next one
-      // goes out now into the other buffer
-      cp_async_wait_all();
-      typename P::Raw curE, curL;
-      // UNCOND_STAGE: read unconditionally (a slot that was not filled for this row is read but never used) - GF1a's
-      // conditionally assigned struct is otherwise kept in local memory by the compiler
-      if (P::UNCOND_STAGE || (qload && enter)) pol.stage_read(stage, 2 * par, curE);
-      if (P::UNCOND_STAGE || (qload && leave)) pol.stage_read(stage, 2 * par + 1, curL);
-      const int yn = yi + 1, yln = yli + 1;
-      if (qload && yn < y_end) {
-        int gxa = gx;  // opaque: the row addresses are formed from the (uniform) plane base here, not carried per thread
-        if constexpr (P::META) asm("" : "+r"(gxa) : "r"(yi));
-        if (yn >= 0 && yn < H) pol.stage_issue(stage, 2 * (par ^ 1), yn, gxa);
-        if (yln >= y_first) pol.stage_issue(stage, 2 * (par ^ 1) + 1, yln, gxa);
-      }
-      cp_async_commit();
-      unsigned cm = meta;  // opaque copy: keeps the four bit tests of the partial-quad path out of spill slots
-      if constexpr (P::META) asm("" : "+r"(cm) : "r"(yi));  // not volatile (free to schedule), tied to the row so that it stays in the loop
-      cm >>= 28;
-      if (cm == 0xfu) {  // whole quad inside the image: straight-line code
-        if (enter) pol.template accum<+1, true>(curE, cm, Vi, Vd);
-        if (leave) pol.template accum<-1, true>(curL, cm, Vi, Vd);
-      } else if (qload) {
-        if (enter) pol.template accum<+1, false>(curE, cm, Vi, Vd);
-        if (leave) pol.template accum<-1, false>(curL, cm, Vi, Vd);
-      }
-    } else {
-      mbar_wait(mbar, (unsigned)par);  // phase parity = march row parity
-      if (qload && (enter || leave)) gf_accum_staged<P::NP, NT>(reinterpret_cast<const float4*>(stage), gx >> 2, enter, leave, cmask, Vd);
-    }
-  };
-
-  // ---- prologue: first march row ------------------------------------------------------------------
-  if constexpr (P::PREFETCH) {
-    if (!aux) {
-      int yl = y_begin - 2 * r - 1;
-      if (qload && y_begin >= 0 && y_begin < H) pol.stage_issue(stage, 0, y_begin, gx);
-      if (qload && yl >= y_first) pol.stage_issue(stage, 1, yl, gx);
-      cp_async_commit();
-      acc(y_begin);
-    }
-  } else {
-    if (t == NT) tma_rows(y_begin);
-    if (!aux) acc(y_begin);
-    __syncthreads();
-    if (t == NT) tma_rows(y_begin + 1);
-  }
-
-  // named barrier 1: the workers ARRIVE (they do not wait) once their row is published, the auxiliary warp waits on it
-  auto bar_arrive_published = [&]() { asm volatile("bar.arrive 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
-  auto bar_wait_published = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT + 32 * P::NAUX) : "memory"); };
-  // named barrier 2 (plane readers): the workers arrive when they have consumed the staged rows, the TMA producer waits
-  auto bar_arrive_consumed = [&]() { asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory"); };
-  auto bar_wait_consumed = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); };
-  static_assert(P::DBUF || !P::DELAY, "the delayed window phase reads one published row while the next one is written");
-
-  // window sums and per-pixel work of output row yo (published and scanned during the previous loop iteration)
-  auto window_phase = [&](const int yo) {
-    select_buffer(yo);
-    // ---- window sums and the per-pixel work -----------------------------------------------------------
-    unsigned mrow = meta;  // opaque per-row copy (see the definition of meta)
-    if constexpr (P::META) asm("" : "+r"(mrow) : "r"(yo));
-    if (P::META ? (mrow & 127u) != 0 : oact) {  // output quad
-      // META: the two shared-memory indices are formed from the thread index per row (held across the march they end up
-      // in spill slots)
-      int tq = t;
-      if constexpr (P::META) asm("" : "+r"(tq) : "r"(yo));
-      const int tlo = P::META ? tq - rho : tlo_h, thi = P::META ? tq + rho : thi_h;
-      if constexpr (P::EARLY_ROW == 0) pol.row_begin(yo, gx);
-      if constexpr (P::EARLY_ROW == 2) pol.row_pickup(smem_raw + L::off_row);
-      // integer window sums: all four columns at once (two 16-byte loads per moment), or - for policies
-      // that trade loads for registers (INT_HALF) - two columns per half
-      uint32_t si[P::INT_HALF ? 2 : 4][NIa];
-      auto int_sums = [&](int h) {
-        if (gg.fast) {
-#pragma unroll
-          for (int k = 0; k < NI; k++) {
-            uint32_t Wq = Gi[k * GP + thi - 1] - Gi[k * GP + tlo - 1];
-            uint4 a = Pi[k * NT + tlo];
-            if constexpr (!P::INT_HALF) {
-              uint4 b = Pi[k * NT + thi];
-              si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; si[2][k] = Wq - a.y + b.z; si[3][k] = Wq - a.z + b.w;
-            } else {
-              uint2 b = reinterpret_cast<const uint2*>(Pi + k * NT + thi)[h];
-              if (h == 0) { si[0][k] = Wq + b.x; si[1][k] = Wq - a.x + b.y; }
-              else { si[0][k] = Wq - a.y + b.x; si[1][k] = Wq - a.z + b.y; }
-            }
-          }
-        } else {
-          const uint32_t* Pis = reinterpret_cast<const uint32_t*>(Pi);
-#pragma unroll
-          for (int cc = 0; cc < (P::INT_HALF ? 2 : 4); cc++) {
-            int c = P::INT_HALF ? 2 * h + cc : cc;
-            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
-#pragma unroll
-            for (int k = 0; k < NI; k++) {
-              uint32_t fl = Gi[k * GP + (zl >> 2) - 1] + ((zl & 3) ? Pis[k * NT * 4 + zl - 1] : 0u);
-              uint32_t fh = Gi[k * GP + (zh >> 2) - 1] + ((zh & 3) ? Pis[k * NT * 4 + zh - 1] : 0u);
-              si[cc][k] = fh - fl;
-            }
-          }
-        }
-      };
-      if constexpr (!P::INT_HALF) int_sums(0);
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        if constexpr (P::INT_HALF) int_sums(h);
-        double sd[2][ND];
-        if (gg.fast) {
-#pragma unroll
-          for (int k = 0; k < ND; k++) {
-            const double Gl = Gd[k * GP + tlo - 1];
-            double Wq = Gd[k * GP + thi - 1] - Gl;
-            double2 a01 = Pd01[k * NT + tlo];
-            if (h == 0) {
-              double2 b = Pd01[k * NT + thi];
-              sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a01.x) + b.y;
-            } else {
-              double a2 = Pd2[k * NT + tlo], b2 = Pd2[k * NT + thi];
-              sd[0][k] = (Wq - a01.y) + b2;
-              sd[1][k] = (Gd[k * GP + thi] - Gl) - a2;  // the whole quad thi is inside: totals up to and including it
-            }
-          }
-        } else {
-          const double* P01 = reinterpret_cast<const double*>(Pd01);
-#pragma unroll
-          for (int cc = 0; cc < 2; cc++) {
-            int c = 2 * h + cc;
-            int zl = 4 * t + c - r, zh = 4 * t + c + r + 1;
-#pragma unroll
-            for (int k = 0; k < ND; k++) {
-              // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd2
-              int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-              double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : Pd2[k * NT + (zl >> 2)]);
-              double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : Pd2[k * NT + (zh >> 2)]);
-              sd[cc][k] = (Gd[k * GP + (zh >> 2) - 1] + ph) - (Gd[k * GP + (zl >> 2) - 1] + pl);
-            }
-          }
-        }
-        const unsigned cm = mrow >> 28;
-        int gxo = gx;
-        if constexpr (P::META) asm("" : "+r"(gxo) : "r"(yo));
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          const int c = 2 * h + cc;
-          if (cm & (1u << c)) {  // column gx + c is an image column
-            const int x = gxo + c;
-            const int ny = min(yo + r, H - 1) - max(yo - r, 0) + 1;
-            const int nx = nx_packed ? (int)((mrow >> (7 * c)) & 127u) : min(x + r, W - 1) - max(x - r, 0) + 1;
-            pol.column(cc, yo, x, ny * nx, si[P::INT_HALF ? cc : 2 * h + cc], sd[cc]);
-          }
-        }
-        if (cm & (1u << (2 * h))) pol.store_pair(yo, gxo + 2 * h);
-      }
-    }
-  };
-
-  if constexpr (P::DELAY) {
-    // One loop iteration = one output row, ONE CTA-wide barrier:
-    //   workers: publish(yo) | arrive 1 | add march row yin+1 | arrive 2 | window sums + per-pixel work of row yo-1 | barrier
-    //   aux:     wait 1 (published) | scan the quad totals of row yo | wait 2 (staging consumed) | TMA(yin+2)       | barrier
-    // The scan of row yo has the whole worker phase to finish and is consumed one iteration later, so the workers never
-    // wait for it; the published rows are double-buffered by row parity, which is what makes the delay possible.
-    // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
-    for (int yin = y_begin; yin <= y_end; ++yin) {  // the extra iteration runs the window phase of the last row
-      const int yo = yin - r;
-      if (yo < ys) {  // warm-up rows (uniform across the CTA)
-        if (!aux) acc(yin + 1);
-        if constexpr (!P::PREFETCH) {
-          __syncthreads();
-          if (t == NT) tma_rows(yin + 2);
-        }
-        continue;
-      }
-      const bool pub = yo < ye;  // uniform
-      if (pub) {
-        // ---- publish the quad prefixes and totals -------------------------------------------------------
-        select_buffer(yo);
-        if (qact) {
-  #pragma unroll
-          for (int k = 0; k < NI; k++) {
-            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-            Gi[k * GP + t] = p3;
-          }
-  #pragma unroll
-          for (int k = 0; k < ND; k++) {
-            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-            Pd01[k * NT + t] = make_double2(p0, p1);
-            Pd2[k * NT + t] = p2;
-            Gd[k * GP + t] = p3;
-          }
-        }
-      }
-      if (aux) {
-        if (pub) {
-          bar_wait_published();
-          // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
-          // the auxiliary warps
-          const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
-          constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
-  #pragma unroll
-          for (int rd = 0; rd < RI + RD; rd++) {
-            if (rd % P::NAUX != aw) continue;
-            if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
-            else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
-          }
-        }
-      } else {
-        if (pub) bar_arrive_published();
-        acc(yin + 1);
-        if constexpr (!P::PREFETCH) {
-          // plane readers: the LAST worker warp waits until every worker has consumed the staged rows (named barrier 2,
-          // workers only) and its first lane requests the next ones, which land during the window phase
-          if (t >= NT - 32) {
-            bar_wait_consumed();
-            if (t == NT - 32) tma_rows(yin + 2);
-          } else {
-            bar_arrive_consumed();
-          }
-        }
-        if (yo > ys) window_phase(yo - 1);
-      }
-      __syncthreads();
-    }
-  } else {
-    // invariant at the top: the sums hold the march rows <= yin; row yin+1 has been requested
-    for (int yin = y_begin; yin < y_end; ++yin) {
-      const int yo = yin - r;
-      if (yo < ys) {  // warm-up rows (uniform across the CTA)
-        if (!aux) acc(yin + 1);
-        if constexpr (!P::PREFETCH) {
-          __syncthreads();
-          if (t == NT) tma_rows(yin + 2);
-        }
-        continue;
-      }
-      // ---- publish the quad prefixes and totals -------------------------------------------------------
-      select_buffer(yo);
-      if constexpr (P::EARLY_SCAN) {
-        // quad totals first: as soon as every worker has stored them (named barrier 1, the workers only arrive) the
-        // auxiliary warp starts its scan, while the workers go on with the quad prefixes and the next march row.
-        // The sums are exact, so (V0 + V2) + (V1 + V3) is the last element of the prefix chain bit for bit (and shares no
-        // subexpression with it that the compiler would keep in registers across the hand-off).
-        if (qact) {
-  #pragma unroll
-          for (int k = 0; k < NI; k++) Gi[k * GP + t] = (Vi[0][k] + Vi[2][k]) + (Vi[1][k] + Vi[3][k]);
-  #pragma unroll
-          for (int k = 0; k < ND; k++) Gd[k * GP + t] = (Vd[0][k] + Vd[2][k]) + (Vd[1][k] + Vd[3][k]);
-        }
-        if (aux) bar_wait_published(); else bar_arrive_published();
-        if (qact) {
-  #pragma unroll
-          for (int k = 0; k < NI; k++) {
-            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-          }
-  #pragma unroll
-          for (int k = 0; k < ND; k++) {
-            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k];
-            Pd01[k * NT + t] = make_double2(p0, p1);
-            Pd2[k * NT + t] = p2;
-          }
-        }
-      } else {
-        if (qact) {
-    #pragma unroll
-          for (int k = 0; k < NI; k++) {
-            uint32_t p0 = Vi[0][k], p1 = p0 + Vi[1][k], p2 = p1 + Vi[2][k], p3 = p2 + Vi[3][k];
-            Pi[k * NT + t] = make_uint4(p0, p1, p2, p3);
-            Gi[k * GP + t] = p3;
-          }
-    #pragma unroll
-          for (int k = 0; k < ND; k++) {
-            double p0 = Vd[0][k], p1 = p0 + Vd[1][k], p2 = p1 + Vd[2][k], p3 = p2 + Vd[3][k];
-            Pd01[k * NT + t] = make_double2(p0, p1);
-            Pd2[k * NT + t] = p2;
-            Gd[k * GP + t] = p3;
-          }
-        }
-        __syncthreads();  // A
-      }
-      if (aux) {
-        // prefix over the quad totals, four moments per round (8 lanes each); the rounds alternate between
-        // the auxiliary warps
-        const int seg = lane & 7, mq = lane >> 3, aw = (t - NT) >> 5;
-        constexpr int RI = (NI + 3) / 4, RD = (ND + 3) / 4;
-  #pragma unroll
-        for (int rd = 0; rd < RI + RD; rd++) {
-          if (rd % P::NAUX != aw) continue;
-          if (rd < RI) { const int k0 = 4 * rd; gf_scan_task<uint32_t, uint4>(Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
-          else { const int k0 = 4 * (rd - RI); gf_scan_task<double, double2>(Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
-        }
-      } else {
-        // plane readers that want it: the global loads of row yo's per-pixel inputs go out here, a whole accumulate phase
-        // (and barrier B) before their first use
-        if constexpr (P::EARLY_ROW == 1) { if (oact) pol.row_begin(yo, gx); }
-        if constexpr (P::EARLY_ROW == 2) { if (oact) pol.row_prefetch(smem_raw + L::off_row, yo, gx); }
-        acc(yin + 1);
-      }
-      __syncthreads();  // B
-      if constexpr (!P::PREFETCH) {
-        if (t == NT) tma_rows(yin + 2);  // every worker has consumed the staged rows
-      }
-      window_phase(yo);
-      if constexpr (!P::DBUF) __syncthreads();  // C (with two buffers the barriers A, B of the next row order the reuse)
-    }
-  }
-  pol.finish();
-}
+// coefficient rows: int32 fixed point (gfpipe.cuh: coef_scale)
+#define GP_COEF_T int
+#define GP_COEF_V4 int4
+#define GP_COEF_PACK(a, b, cs) coef_pack_fix(a, b, (cs).sa, (cs).sb)
+#include "gfpipe.cuh"
 
 // geometry + launch -------------------------------------------------------------------------------------
-static GfGeom gf_geometry(int W, int H, int r, int NT) {
+static GfGeom gf_geometry(int W, int H, int r) {
   GfGeom g;
   g.W = W; g.H = H; g.Wp = (W + 3) & ~3; g.r = r;
   g.HL = (r + 3) & ~3;
-  int sw_max = 4 * (NT - 1) - 2 * g.HL;
+  int sw_max = std::min(4 * (GP_NT - 1) - 2 * g.HL, GP_MAXSW);   // quads per strip (ACC) and pixel pairs per strip (SOLVE)
   int strips = cdiv(W, sw_max);
   g.SW = (cdiv(W, strips) + 3) & ~3;
   g.NQ = 1 + (2 * g.HL + g.SW) / 4;
@@ -1639,16 +747,12 @@ static GfGeom gf_geometry(int W, int H, int r, int NT) {
   return g;
 }
 
-static_assert(GfSmem<PolGF2b>::bytes + 1024 <= (227 * 1024) / 2, "GF2b runs two CTAs per SM");
-static_assert(GfSmem<PolGF1a>::bytes <= 227 * 1024 && GfSmem<PolGF1b>::bytes <= 227 * 1024 && GfSmem<PolGF2a>::bytes <= 227 * 1024, "shared memory");
-
 template <class P>
-static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, int W, int H, int r) {
-  static_assert(P::NT <= GF_GP, "quad-total rows hold one entry per thread");
-  GfGeom gg = gf_geometry(W, H, r, P::NT);
+static int gp_launch(uwip_ctx* ctx, const char* tag, int func_id, const GfCommon& gc, int n, int W, int H, int r) {
+  GfGeom gg = gf_geometry(W, H, r);
   int strips = cdiv(W, gg.SW);
   // vertical segments: fill the machine (tail of the last wave) against the 2r warm-up rows per segment
-  int slots = ctx->sm_count * P::MINB;
+  int slots = ctx->sm_count;
   int tasks = strips * n;
   int best = 1;
   double best_eff = 0.0;
@@ -1661,16 +765,14 @@ static int gf_launch(uwip_ctx* ctx, const char* tag, const GfCommon& gc, int n, 
   }
   gg.seg_h = cdiv(H, best);
   int segs = cdiv(H, gg.seg_h);
-  size_t smem = GfSmem<P>::bytes;
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
-    UWIP_CUDA(ctx, cudaFuncSetAttribute(gf_march_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  size_t smem = GpSmem<P>::bytes;
+  UWIP_CUDA(ctx, uwip_func_smem(ctx, func_id, gp_kernel<P>, smem));
   dim3 grid(strips, segs, n);
-  UWIP_LAUNCH(ctx, tag, gf_march_kernel<P>, grid, P::NT + 32 * P::NAUX, smem, gc, gg);
+  UWIP_LAUNCH(ctx, tag, gp_kernel<P>, grid, GP_THREADS, smem, gc, gg);
   return UWIP_OK;
 }
+static_assert(GpSmem<PipGFq>::bytes <= 227 * 1024 && GpSmem<PipGF1a>::bytes <= 227 * 1024 && GpSmem<PipGF2a>::bytes <= 227 * 1024 && GpSmem<PipGF1b>::bytes <= 227 * 1024 &&
+              GpSmem<PipGF2b>::bytes <= 227 * 1024, "shared memory");
 
 // -------------------------------------------------------------------------------------------------
 // E: restored -> R8, I8 -> YCrCb joint min / max (BGDehaze.py:75-80); stores (Yi, Cri, Cbi, Yj)
@@ -1735,6 +837,7 @@ __global__ void __launch_bounds__(256) stab_kernel(const FrameState* __restrict_
 // S per pixel as an f32 plane: GF2a then reads it through the same staged row copies as the guide instead
 // of gathering from the table inside the march (f32 keeps 2^-24 relative: far inside the 1e-5 budget).
 __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) {
+  const double pscale = GP_PSCALE;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
   const FrameState& s = g.fs[f];
@@ -1742,21 +845,26 @@ __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) 
   const uint32_t ysub = a | (a << 8) | (a << 16) | (b << 24);
   const uint32_t* ycc = g.ycc + (size_t)f * n_pp;
   const double* stab = g.stab + (size_t)f * 65536;
-  float* sp = g.splane + (size_t)f * n_pp;
+  uint32_t* sp = reinterpret_cast<uint32_t*>(g.splane) + (size_t)f * n_pp;
   const size_t n_q = n_pp / 4;
+  bool nan_seen = false;
   for (size_t qi = (size_t)blockIdx.x * 256 + threadIdx.x; qi < n_q; qi += (size_t)gridDim.x * 256) {
     uint4 yw = __ldg(reinterpret_cast<const uint4*>(ycc) + qi);
-    float o[4];
+    uint32_t o[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t w = quad_get(yw, c);
       // pad columns hold zeros: keep them away from the table (their S is never used)
       bool pad = (w & 255u) < a || (w >> 24) < b;
       w -= ysub;
-      o[c] = pad ? 0.f : (float)grid_round<28>(__ldg(stab + (((w & 255u) << 8) | (w >> 24))));
+      // S = 0/0 where Yi' = Yj' = 0: the NaN reaches every output of the reference -> flag the frame
+      const double S = pad ? 0.0 : __ldg(stab + (((w & 255u) << 8) | (w >> 24)));
+      if (!(S == S)) nan_seen = true;
+      o[c] = (S == S) ? __double2uint_rn(fmin(S, GP_S_PMAX) * pscale) : 0u;
     }
-    reinterpret_cast<float4*>(sp)[qi] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(sp)[qi] = make_uint4(o[0], o[1], o[2], o[3]);
   }
+  if (__any_sync(0xffffffffu, nan_seen) && (threadIdx.x & 31) == 0) atomicOr(&g.fs[f].nan_flag, 1u);
 }
 
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
@@ -1818,7 +926,7 @@ __global__ void __launch_bounds__(256, 4) final_kernel(GfCommon g, int W, int H,
 // Batch size for which the strips of the one-CTA-per-SM marches make one full wave (4K: 148 SMs / 5 strips =
 // 29 frames); the host-buffer pipeline cuts its sub-batches in multiples of it.
 int dehaze_wave_frames(const uwip_ctx* ctx, int w) {
-  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40, PolGF1a::NT);
+  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
   return std::max(1, ctx->sm_count / cdiv(w, g.SW));
 }
 
@@ -1827,6 +935,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   UWIP_REQUIRE(ctx, n >= 1 && W >= 1 && H >= 1, "bad size");
   UWIP_REQUIRE(ctx, p.window >= 1 && p.window <= WK_MAXWIN, "window must be 1..33");
   UWIP_REQUIRE(ctx, p.radius >= 1 && p.radius <= 160, "radius must be 1..160");
+  UWIP_REQUIRE(ctx, p.eps > 0.0 && p.tmin <= 1.0, "eps must be positive and tmin <= 1");
   UWIP_REQUIRE(ctx, (size_t)W * H < (1ull << 31), "frame too large");
   UWIP_REQUIRE(ctx, !dbg || n == 1, "stage outputs are single-frame");
   size_t n_px = (size_t)W * H;
@@ -1858,22 +967,14 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
       int PL = std::max(wmax / 2, wmin / 2), PR = std::max(wmax - 1 - wmax / 2, wmin - 1 - wmin / 2);
       int RW = WK_TX + PL + PR, RH = WK_TY + PL + PR;
       size_t smem = ((size_t)2 * RW * RH + (size_t)3 * RH * WK_TX) * 4;
-      static size_t attr = 0;
-      if (smem > attr) {
-        UWIP_CUDA(ctx, cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-      }
+      UWIP_CUDA(ctx, uwip_func_smem(ctx, FUNC_WINDOW, window_kernel, smem));
       UWIP_LAUNCH(ctx, "dz_window", window_kernel, gridw, WK_THREADS, smem, d_src, W, H, Wp, wmax, fs, d_kq, d_mg, d_part);
       UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_part, fs, 1, 0);
     }
     // ... but refined_t() is always called without w (BGDehaze.py:52): the transmission and the
     // background light inside transmission_map use the 15x15 window
     size_t smemf = ((size_t)2 * WF_RH * WF_PP + (size_t)3 * WF_RH * WF_HP) * 4;
-    static bool attrf = false;
-    if (!attrf) {
-      UWIP_CUDA(ctx, cudaFuncSetAttribute(window15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
-      attrf = true;
-    }
+    UWIP_CUDA(ctx, uwip_func_smem(ctx, FUNC_WINDOW15, window15_kernel, smemf));
     UWIP_LAUNCH(ctx, "dz_window", window15_kernel, gridf, 256, smemf, d_src, W, H, Wp, fs, d_kq, d_mg, d_part);
     UWIP_LAUNCH(ctx, "dz_bglight", bglight_finish_kernel, n, 256, 0, d_src, W, H, d_part, n_partf, fs, wmax == WK_TWIN ? 1 : 0, 1);
   }
@@ -1887,8 +988,8 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   GfCommon gc;
   gc.kq = d_kq; gc.mg = d_mg; gc.ycc = d_ycc; gc.stab = d_stab; gc.splane = d_sp; gc.ab = d_ab; gc.J = d_J; gc.refS = d_refS; gc.fs = fs;
   gc.eps = p.eps; gc.tmin = p.tmin; gc.dbg_tref = dbg ? dbg->t_ref : nullptr;
-  UWIP_CHECK(gf_launch<PolGF1a>(ctx, "dz_gf1a", gc, n, W, H, p.radius));
-  UWIP_CHECK(gf_launch<PolGF1b>(ctx, "dz_gf1b", gc, n, W, H, p.radius));
+  UWIP_CHECK(gp_launch<PipGF1a>(ctx, "dz_gf1a", FUNC_GF1A, gc, n, W, H, p.radius));
+  UWIP_CHECK(gp_launch<PipGF1b>(ctx, "dz_gf1b", FUNC_GF1B, gc, n, W, H, p.radius));
   if (dbg && dbg->stop_after == 3) return UWIP_OK;
   int gx = std::max(1, std::min((int)((n_pp / 4 + 1023) / 1024), std::max(1, ctx->sm_count * 24 / n)));
   dim3 grid_e(gx, n);
@@ -1897,8 +998,82 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   dim3 grid_s(256, n);
   UWIP_LAUNCH(ctx, "dz_stab", stab_kernel, grid_s, 256, 0, fs, d_stab);
   UWIP_LAUNCH(ctx, "dz_splane", splane_kernel, grid_e, 256, 0, gc, H, Wp);
-  UWIP_CHECK(gf_launch<PolGF2a>(ctx, "dz_gf2a", gc, n, W, H, p.radius));
-  UWIP_CHECK(gf_launch<PolGF2b>(ctx, "dz_gf2b", gc, n, W, H, p.radius));
+  UWIP_CHECK(gp_launch<PipGF2a>(ctx, "dz_gf2a", FUNC_GF2A, gc, n, W, H, p.radius));
+  UWIP_CHECK(gp_launch<PipGF2b>(ctx, "dz_gf2b", FUNC_GF2B, gc, n, W, H, p.radius));
   UWIP_LAUNCH(ctx, "dz_final", final_kernel, grid_e, 256, 0, gc, W, H, Wp, d_dst, dbg ? dbg->out : (double*)nullptr, d_flags);
+  return UWIP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// stage entry points of guidedfilter.py (stage-wise parity; not on the throughput path)
+// -------------------------------------------------------------------------------------------------
+// boxfilter(I, r) guidedfilter.py:23-51: (2r+1)^2 window SUM, windows truncated at the borders; float64.  Two
+// separable passes of direct sums (the reference takes differences of cumulative sums: 2e-11 relative apart).
+__global__ void __launch_bounds__(256) box_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int W, int H, int r) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const double* row = src + (size_t)y * W;
+  double s = 0.0;
+  for (int k = max(x - r, 0); k <= min(x + r, W - 1); k++) s += row[k];
+  dst[(size_t)y * W + x] = s;
+}
+__global__ void __launch_bounds__(256) box_cols_kernel(const double* __restrict__ src, double* __restrict__ dst, int W, int H, int r) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  double s = 0.0;
+  for (int k = max(y - r, 0); k <= min(y + r, H - 1); k++) s += src[(size_t)k * W + x];
+  dst[(size_t)y * W + x] = s;
+}
+int boxfilter_f64_dev(uwip_ctx* ctx, const double* d_src, double* d_tmp, double* d_dst, int W, int H, int r) {
+  UWIP_REQUIRE(ctx, W >= 1 && H >= 1 && r >= 0, "bad size");
+  dim3 grid(cdiv(W, 256), H);
+  UWIP_LAUNCH(ctx, "box_rows", box_rows_kernel, grid, 256, 0, d_src, d_tmp, W, H, r);
+  UWIP_LAUNCH(ctx, "box_cols", box_cols_kernel, grid, 256, 0, (const double*)d_tmp, d_dst, W, H, r);
+  return UWIP_OK;
+}
+
+// guided_filter(I, p, r, eps) guidedfilter.py:54-103 for a guide of the form I = guide8 / range (every guide on the path
+// is: main.py:17, BGDehaze.py:77-80).  The packed guide and the fixed-point p feed the same two marches as the third
+// filter of adaptiveExp_map.
+__global__ void __launch_bounds__(256) gfq_pack_kernel(const uint8_t* __restrict__ guide, const double* __restrict__ p, int W, int H, int Wp,
+                                                       uint32_t* __restrict__ ycc, uint32_t* __restrict__ sp, FrameState* fs) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= Wp) return;
+  uint32_t g = 0, P = 0;
+  bool bad = false;
+  if (x < W) {
+    const uint8_t* q = guide + ((size_t)y * W + x) * 3;
+    g = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+    const double v = p[(size_t)y * W + x];
+    bad = !(v >= 0.0 && v <= GP_S_PMAX);
+    P = bad ? 0u : __double2uint_rn(v * GP_PSCALE);
+  }
+  ycc[(size_t)y * Wp + x] = g;
+  sp[(size_t)y * Wp + x] = P;
+  if (bad) atomicOr(&fs[0].nan_flag, 2u);
+}
+__global__ void gfq_state_kernel(FrameState* fs, int range) {
+  FrameState& s = fs[0];
+  s.yi_min = 0; s.yi_max = (unsigned)range; s.yj_min = 0; s.yj_max = (unsigned)range;
+  s.kmin = 0; s.kmax = (unsigned)range;
+}
+int guided_filter_u8_dev(uwip_ctx* ctx, const uint8_t* d_guide, const double* d_p, double* d_q, int W, int H, int range, int r, double eps,
+                         FrameState* fs) {
+  UWIP_REQUIRE(ctx, W >= 1 && H >= 1 && r >= 1 && r <= 160 && range >= 1 && range <= 255 && eps > 0.0, "bad argument");
+  const int Wp = (W + 3) & ~3;
+  const size_t n_pp = (size_t)Wp * H;
+  uint32_t* d_ycc = (uint32_t*)uwip_slot(ctx, SLOT_YCC, n_pp * 4);
+  float* d_sp = (float*)uwip_slot(ctx, SLOT_SPLANE, n_pp * 4);
+  float* d_ab = (float*)uwip_slot(ctx, SLOT_AB, 8 * n_pp * 4);
+  if (!d_ycc || !d_sp || !d_ab) return UWIP_ERR_NOMEM;
+  UWIP_CHECK(frame_state_reset(ctx, fs, 1));
+  UWIP_LAUNCH(ctx, "gfq_state", gfq_state_kernel, 1, 1, 0, fs, range);
+  dim3 grid(cdiv(Wp, 256), H);
+  UWIP_LAUNCH(ctx, "gfq_pack", gfq_pack_kernel, grid, 256, 0, d_guide, d_p, W, H, Wp, d_ycc, reinterpret_cast<uint32_t*>(d_sp), fs);
+  GfCommon gc;
+  memset(&gc, 0, sizeof(gc));
+  gc.ycc = d_ycc; gc.splane = d_sp; gc.ab = d_ab; gc.fs = fs; gc.eps = eps; gc.tmin = 0.0; gc.dbg_tref = d_q;
+  UWIP_CHECK(gp_launch<PipGF2a>(ctx, "dz_gf2a", FUNC_GF2A, gc, 1, W, H, r));
+  UWIP_CHECK(gp_launch<PipGFq>(ctx, "gfq_out", FUNC_GFQ, gc, 1, W, H, r));
   return UWIP_OK;
 }
