@@ -196,9 +196,10 @@ def run_reference(args):
         "impl": "reference", "metric": "chain_frames_per_s_4k", "value": fps4k, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": dict(chain_config(args.width, args.height, args.frames),
-                       reference_sample="each step = %d synthetic %dx%d frames (1/16 of a 4K frame each) through the CPU chain on %d "
-                                        "processes, frames/s scaled by pixel count to 3840x2160" % (procs, sw, sh, procs)),
+        "config": chain_config(args.width, args.height, args.frames),   # the arm's config (the driver compares the two arms' dictionaries) ...
+        # ... and what a step of THIS arm actually ran: a bounded sample of that workload, scaled by pixel count
+        "ran": "each step = %d synthetic %dx%d frames (1/16 of the pixels of a 4K frame each) through the CPU chain on %d processes; "
+               "frames/s scaled by pixel count to 3840x2160" % (procs, sw, sh, procs),
         "cpu_baseline": {"value": fps4k, "unit": "frames/s", "cores": procs, "kind": "port",
                          "sample": "%d synthetic %dx%d frames per step on %d processes (cv2 for the OpenCV calls, numpy fp64 "
                                    "restatement for bgdehaze), scaled by pixel count to 3840x2160" % (procs, sw, sh, procs)},

@@ -633,6 +633,63 @@ def gaussian_blur3(plane: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------------------
 
 
+def _aclahe_knee(x: np.ndarray, y: np.ndarray) -> int:
+    """DerivadaY / DerivadaX / Curvatura of modules/aclahe/python/functions.py:49-93: double-exponential fit of the 49
+    samples, cubic spline through 25 points of the fit, curvature |x'y'' - y'x''| / (x'^2 + y'^2)^1.5 at 49 points,
+    index of its maximum (used directly as the clip limit, ACLAHE.py:92-96)."""
+    from scipy.interpolate import splev, splrep
+    from scipy.optimize import curve_fit
+
+    def f(t, p0, p1, p2, p3):
+        return p0 * np.exp(-p1 * t) + p2 * np.exp(-p3 * t)
+
+    u = np.linspace(1, 49, 49)
+    x22 = np.linspace(1, 25, 25)
+    x222 = np.linspace(1, 25, 49)
+    d = []
+    for v in (y, x):
+        popt, _ = curve_fit(f, u, v, (7, 0.4, 0.9, 5))
+        tck = splrep(x22, f(x22, *popt))
+        d.append((splev(x222, tck, der=1), splev(x222, tck, der=2)))
+    (y1, y2), (x1, x2) = d
+    k = np.sqrt((x1 * y2 - y1 * x2) ** 2) / np.sqrt((x1 ** 2 + y1 ** 2) ** 3)
+    return int(np.argmax(k))
+
+
+def parametros_aclahe(img: np.ndarray, loop: str = "repaired"):
+    """ParametrosACLAHE of modules/aclahe/python/ACLAHE.py:9-129 -> (BS, CL, entropies[5][50]).
+    loop='as_committed': the sweep body as it stands in the file (lines 42-45 outside `for i in cl`): the curves handed to
+    the knee search are all zero, the clip limit degenerates to 0.  loop='repaired': every clip limit evaluated."""
+    import warnings
+
+    blur = gaussian_blur3(img)                                     # ACLAHE.py:15
+    bl = (2, 4, 8, 16, 32)
+    cl = np.arange(0, 25, 0.5)
+    ent = np.zeros((5, 50), np.float32)
+    if loop == "repaired":
+        knees = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for j, k in enumerate(bl):
+                ent[j] = [entropy_py(clahe_apply(blur, float(c), k, k)) for c in cl]
+                row_x = np.zeros(51, np.float32)
+                row_y = np.zeros(51, np.float32)
+                row_x[1:51] = cl
+                row_y[1:51] = ent[j]
+                knees.append(_aclahe_knee(row_x[2:51], row_y[2:51]))   # graficar drops the first two columns
+        d = max(knees)
+    elif loop == "as_committed":
+        d = 0
+    else:
+        raise ValueError(loop)
+    res = np.zeros((2, 5), np.float16)                             # ACLAHE.py:102: float16 table
+    for m, k in enumerate(bl):
+        res[0, m] = k
+        res[1, m] = entropy_py(clahe_apply(blur, float(d), k, k))
+    w = int(np.flatnonzero(res[1] == res[1].max())[-1])            # last arg-max wins (ACLAHE.py:117-121)
+    return int(round(float(res[0, w]))), d, ent
+
+
 def _window_reduce(a: np.ndarray, w: int, op, pad_value) -> np.ndarray:
     """w x w window reduction centred like `padded[y:y+w, x:x+w]` with padwidth floor(w/2)."""
     pw = w // 2

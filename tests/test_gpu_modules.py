@@ -232,3 +232,75 @@ def test_two_devices_in_one_process():
         c.close()
     assert (outs[0] == outs[1]).all()
     torch.cuda.set_device(0)
+
+
+# ---- command-line shims (histretch.cpp:61-271, aclahe.cpp:64-226, bgdehaze/main.py:22-33) --------------------
+def _write_ppm(path, bgr):
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (bgr.shape[1], bgr.shape[0]))
+        f.write(np.ascontiguousarray(bgr[..., ::-1]).tobytes())
+
+
+def _read_ppm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P6"
+        w, h = map(int, f.readline().split())
+        assert f.readline().strip() == b"255"
+        return np.frombuffer(f.read(), np.uint8).reshape(h, w, 3)[..., ::-1].copy()
+
+
+def test_cpp_cli_shims(tmp_path):
+    """The histretch / aclahe binaries built by shims/check.sh (stand-in OpenCV: imread / imwrite speak PPM)."""
+    import subprocess
+
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uwimageproc_b200", "shims")
+    exe = os.path.join(shims, "histretch")
+    if not os.path.exists(exe):
+        subprocess.run(["bash", os.path.join(shims, "check.sh")], check=True, capture_output=True)
+    fr = O.synth_frame(0x5EED0001, 3, 200, 120)
+    src, dst = str(tmp_path / "in.ppm"), str(tmp_path / "out.ppm")
+    _write_ppm(src, fr)
+    r = subprocess.run([exe, src, dst, "-c=HV", "-cuda=1", "-time=1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Execution Time GPU :" in r.stdout and "Channel[1]: V" in r.stdout and "hS: saving to disk" in r.stdout
+    assert (_read_ppm(dst) == O.histretch_frame(fr, "HV", 2, 98)).all()
+    r = subprocess.run([exe, src, dst, "-literal=1", "-c=Vr"], capture_output=True, text=True)   # as written + an unknown letter
+    assert r.returncode == 0 and "Option r not recognized, skipping..." in r.stdout
+    assert (_read_ppm(dst) == O.histretch_frame(fr, "V", 2, 98, order="literal")).all()
+    r = subprocess.run([exe, src, dst], capture_output=True, text=True)                          # default -c=r: no-op (SURVEY H3)
+    assert r.returncode == 0 and (_read_ppm(dst) == fr).all()
+    exe = os.path.join(shims, "aclahe")
+    r = subprocess.run([exe, src, dst, "-bs=8", "-cl=2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    table = [l.split() for l in r.stdout.splitlines() if len(l.split()) == 51]
+    assert len(table) == 5
+    v = fr.max(axis=2)
+    for i, bs in enumerate((2, 4, 8, 16, 32)):
+        for j in (0, 4, 50):
+            want = float(O.entropy_cpp(O.clahe_apply(v, 0.5 * j, bs, bs)))
+            assert abs(float(table[i][j]) - want) < 2e-5, (bs, j)
+    assert (_read_ppm(dst) == O.aclahe_frame(fr, 2.0, 8, 8)).all()
+
+
+def test_python_cli_shims(tmp_path, capsys):
+    cv2 = pytest.importorskip("cv2")
+    from uwimageproc_b200.cli import aclahe as CA
+    from uwimageproc_b200.cli import bgdehaze_main as CB
+    from uwimageproc_b200.cli import histretch as CH
+
+    fr = O.synth_frame(0x5EED0001, 4, 240, 136)
+    src, dst = str(tmp_path / "in.png"), str(tmp_path / "out.png")
+    cv2.imwrite(src, fr)
+    assert CH.main([src, dst, "-c=V", "-time=1", "-cuda=0"]) == 0
+    out = capsys.readouterr().out
+    assert "Execution Time GPU :" in out and "Channel: V" in out and "no CPU path" in out
+    assert (cv2.imread(dst) == O.histretch_frame(fr, "V", 2, 98)).all()
+    assert CH.main([src]) == 0 and "Complete options are:" in capsys.readouterr().out
+    z = np.load(os.path.join(GOLD, "crowd_crop.npz"))
+    g_src = str(tmp_path / "grey.png")
+    cv2.imwrite(g_src, z["img"])
+    assert CA.main([g_src, dst, "-grey=1", "-loop=as_committed"]) == 0
+    assert "BS = " in capsys.readouterr().out
+    d_dst = str(tmp_path / "res" / "dehazed.png")
+    assert CB.main(["--src", src, "--dest", d_dst, "-w", "15"]) == 0
+    assert np.abs(cv2.imread(d_dst).astype(int) - O.bgdehaze_frame(fr, 15)[1].astype(int)).max() <= 1

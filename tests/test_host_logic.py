@@ -169,3 +169,20 @@ def test_bench_reference_arm_prints_one_json_line():
     import bench
 
     assert d["config"] == bench.chain_config(3840, 2160, 256)
+
+
+def test_cli_argument_conventions():
+    """The CLI shims keep cv::CommandLineParser's `-key=value` convention and the reference's defaults (histretch.cpp:68-74)."""
+    from uwimageproc_b200.cli._args import parse
+
+    keys = {"c": ("r", str), "cuda": (1, int), "time": (0, int), "help": (False, bool)}
+    pos, opt, err = parse(["in.jpg", "out.jpg", "-c=HV", "-cuda=0", "--time=1", "-unknown=3"], keys)
+    assert pos == ["in.jpg", "out.jpg"] and opt["c"] == "HV" and opt["cuda"] == 0 and opt["time"] == 1 and not err
+    pos, opt, err = parse(["a", "b"], keys)
+    assert opt["c"] == "r" and opt["time"] == 0          # the reference's default letter is the unrecognised lowercase r
+    assert parse(["-h"], keys)[1]["help"] is True
+    assert parse(["a", "b", "-time=x"], keys)[2]
+    from uwimageproc_b200.cli import aclahe, bgdehaze_main, histretch
+
+    assert histretch.main([]) == 0 and aclahe.main([]) == 0   # help paths need no GPU
+    assert bgdehaze_main.get_filenames("/nonexistent") == []

@@ -1,5 +1,6 @@
 """Pins oracle/uwip_oracle.py (pure numpy) to the golden vectors that oracle/make_golden.py produced
 from cv2 4.13.0 and the reference's own Python files.  CPU only."""
+import json
 import os
 
 import numpy as np
@@ -206,3 +207,17 @@ def test_histretch_literal_order_is_hsv_round_trip():
     # 'R' maps to plane 0 which is BLUE in OpenCV's BGR order
     out = O.histretch_frame(fr, "R", 2, 98)
     assert (out[..., 0] == O.img_channel_stretch(fr[..., 0], 2, 98)).all() and (out[..., 1:] == fr[..., 1:]).all()
+
+
+def test_parametros_aclahe_k4():
+    """the oracle's restatement of ACLAHE.py:9-129 against what the reference's own ACLAHE.py / functions.py
+    returned in the build container for crowd.png (tests/golden/crowd_full.npz, oracle/make_golden_aclahe.py)."""
+    pytest.importorskip("scipy")
+    z = np.load(os.path.join(GOLD, "crowd_full.npz"))
+    img = z["img"]
+    assert O.crc32(img) == json.load(open(os.path.join(GOLD, "kat.json")))["entropy"]["crowd_crc"]
+    bs, cl, _ = O.parametros_aclahe(img, "as_committed")
+    assert (bs, cl) == tuple(int(v) for v in z["as_committed"]) == (8, 0)
+    bs, cl, ent = O.parametros_aclahe(img, "repaired")
+    assert np.abs(ent - z["entropies"]).max() < 2e-6
+    assert (bs, cl) == tuple(int(v) for v in z["repaired"]) == (4, 7)

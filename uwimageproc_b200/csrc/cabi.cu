@@ -8,6 +8,16 @@
 
 #include "common.cuh"
 
+// Every entry point runs on the context's device and puts the caller's current device back when it returns (the library
+// is used next to other CUDA code - torch, OpenCV - whose current device it must not change).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 static thread_local std::string g_create_err;
 
 const char* uwip_set_err(uwip_ctx* ctx, const char* fmt, ...) {
@@ -81,6 +91,7 @@ int uwip_create(int device, uwip_ctx** out) {
     return UWIP_ERR_INVALID;
   }
   cudaDeviceProp prop;
+  DeviceGuard guard(device);   // the caller's current device is put back when uwip_create returns
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
     uwip_set_err(nullptr, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     return UWIP_ERR_CUDA;
@@ -111,12 +122,15 @@ int uwip_create(int device, uwip_ctx** out) {
 
 void uwip_destroy(uwip_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (int i = 0; i < uwip_ctx::kSlots; i++)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -232,10 +246,8 @@ static int stage_out(uwip_ctx* ctx, const uint8_t* d, uint8_t* dst, size_t pitch
   return UWIP_OK;
 }
 #define CTX_GUARD(ctx)                          \
-  do {                                          \
-    if (!(ctx)) return UWIP_ERR_INVALID;        \
-    cudaSetDevice((ctx)->device);               \
-  } while (0)
+  if (!(ctx)) return UWIP_ERR_INVALID;          \
+  DeviceGuard uwip_device_guard__((ctx)->device)
 
 static int check_percentiles(uwip_ctx* ctx, int lo, int hi) {
   if (!(0 <= lo && lo < hi && hi <= 100)) {
@@ -592,6 +604,20 @@ static int chain_sub(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int m,
   return dehaze_frames_dev(ctx, tmp, d_dst, m, w, h, p.dehaze, true, fs, nullptr, flags);
 }
 
+// size every workspace slot a sub-batch of m frames touches (the slots only grow: a later, smaller sub-batch reuses them)
+static int chain_reserve(uwip_ctx* ctx, int m, int w, int h, const uwip_chain_params& p) {
+  const size_t fbytes = (size_t)w * h * 3, n_pp = (size_t)((w + 3) & ~3) * h;
+  const size_t ntile = (size_t)m * std::max(1, p.tiles_x) * std::max(1, p.tiles_y);
+  const struct { int slot; size_t bytes; } want[] = {
+      {SLOT_TMP_FRAME, fbytes * m}, {SLOT_HIST, (size_t)m * 256 * 4}, {SLOT_LUT, (size_t)m * 256 * 4},
+      {SLOT_TILEHIST, ntile * 256 * 4}, {SLOT_TILELUT, ntile * 256 + 16}, {SLOT_MISC, 256},
+      {SLOT_KQ, m * n_pp * 4}, {SLOT_MPLANES, m * n_pp}, {SLOT_YCC, m * n_pp * 4}, {SLOT_STAB, (size_t)m * 65536 * 8},
+      {SLOT_SPLANE, m * n_pp * 4}, {SLOT_AB, m * n_pp * 32}, {SLOT_J, m * n_pp * 8}, {SLOT_REFS, m * n_pp * 4}};
+  for (const auto& e : want)
+    if (!uwip_slot(ctx, e.slot, e.bytes)) return UWIP_ERR_NOMEM;
+  return UWIP_OK;
+}
+
 static int chain_check(uwip_ctx* ctx, const uwip_chain_params* p, int n, int w, int h) {
   UWIP_REQUIRE(ctx, p, "null params (use uwip_chain_defaults)");
   UWIP_REQUIRE(ctx, n > 0 && w > 0 && h > 0, "bad size");
@@ -649,19 +675,23 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   uint8_t* din[2] = {(uint8_t*)uwip_slot(ctx, SLOT_CHAIN_IN0, fbytes * nb), (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_IN1, fbytes * nb)};
   uint8_t* dout[2] = {(uint8_t*)uwip_slot(ctx, SLOT_CHAIN_OUT0, fbytes * nb), (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_OUT1, fbytes * nb)};
   if (!fs || !flags || !din[0] || !din[1] || !dout[0] || !dout[1]) return UWIP_ERR_NOMEM;
-  cudaStream_t s_in, s_out;
-  UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  // copy streams and events live in the context (created on first use, destroyed with it)
+  if (!ctx->s_in) UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  if (!ctx->s_out) UWIP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  cudaStream_t s_in = ctx->s_in, s_out = ctx->s_out;
   int nsub = (int)sizes.size();
-  std::vector<cudaEvent_t> ev_in(nsub), ev_comp(nsub), ev_out(nsub);
-  for (int i = 0; i < nsub; i++) {
-    cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+  while ((int)ctx->ev_pool.size() < 3 * nsub + 1) {
+    cudaEvent_t e;
+    UWIP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ev_pool.push_back(e);
   }
+  cudaEvent_t* ev_in = ctx->ev_pool.data();
+  cudaEvent_t* ev_comp = ev_in + nsub;
+  cudaEvent_t* ev_out = ev_comp + nsub;
+  cudaEvent_t ev_start = ctx->ev_pool[3 * nsub];
+  // the workspace of the largest sub-batch is sized before the pipeline starts: growing a slot synchronises and frees
+  UWIP_CHECK(chain_reserve(ctx, nb, w, h, *p));
   int rc = UWIP_OK;
-  cudaEvent_t ev_start;
-  cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
   cudaEventRecord(ev_start, ctx->stream);  // order after whatever the caller queued on the context stream
   cudaStreamWaitEvent(s_in, ev_start, 0);
   size_t first = 0;
@@ -681,10 +711,6 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
     first += (size_t)m;
   }
   cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(s_out);
-  for (int i = 0; i < nsub; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
-  cudaEventDestroy(ev_start);
-  cudaStreamDestroy(s_in);
-  cudaStreamDestroy(s_out);
   if (rc != UWIP_OK) return rc;
   cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   if (e != cudaSuccess) { uwip_set_err(ctx, "chain pipeline: %s", cudaGetErrorString(e)); return UWIP_ERR_CUDA; }

@@ -27,7 +27,8 @@ struct uwip_ctx {
   int64_t launches = 0;
   bool profiling = false;
   std::vector<ProfRec> prof;
-  std::vector<cudaEvent_t> ev_pool;
+  std::vector<cudaEvent_t> ev_pool;       // timing-disabled events of the host-buffer pipeline, created on demand, reused
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-buffer pipeline (created on first use)
   std::string err;
   // named, grow-only device buffers
   static const int kSlots = 32;
