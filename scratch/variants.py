@@ -6,10 +6,9 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "base": [],
-    "nopark": ["-DGP_PARK=0"],
-    "acc152": ["-DGP_GF1A_ACC_REGS=152"],
-    "acc136": ["-DGP_GF1A_ACC_REGS=136"],
+    "pipe": ["-DGP_GF1A_ACC_REGS=152"],
+    "nopipe": ["-DGP_GF1A_ACC_REGS=152", "-DGP_PIPE_A=0", "-DGP_PIPE_B=0"],
+    "pipe_a104": ["-DGP_GF1A_ACC_REGS=152", "-DGP_GF2A_ACC_REGS=104"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 

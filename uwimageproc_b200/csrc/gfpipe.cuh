@@ -28,8 +28,14 @@
 #ifndef GP_PARK
 #define GP_PARK 1          // mbarrier waits carry a suspend-time hint
 #endif
+#ifndef GP_EXP_SKIP_SOLVE
+#define GP_EXP_SKIP_SOLVE 0   // timing experiment: SOLVE loads its window sums but skips the per-pixel work
+#endif
+#ifndef GP_EXP_SKIP_ACC
+#define GP_EXP_SKIP_ACC 0     // timing experiment: ACC skips the accumulate (publishes stale sums)
+#endif
 #ifndef GP_GF1A_ACC_REGS
-#define GP_GF1A_ACC_REGS 144
+#define GP_GF1A_ACC_REGS 152   // measured: 152 / 104 beats 144 / 112 by 1.5 % and 136 / 120 by 14 % (profiles/r2_summary.md)
 #endif
 #ifndef GP_GF2A_ACC_REGS
 #define GP_GF2A_ACC_REGS 120
@@ -260,13 +266,13 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
       }
       cp_async_commit();
       // one row at a time (the raw quad of the other row is not held meanwhile)
-      if (qload && enter) {
+      if (qload && enter && !(GP_EXP_SKIP_ACC && yin > g.y_begin + 4)) {
         typename Acc::Raw cur;
         acc.stage_read(stage_in, 2 * par, cur, t);
         if (cmask == 0xfu) acc.template accum<+1, true>(cur, cmask, Vi, Vl);  // whole quad inside the image: straight-line code
         else acc.template accum<+1, false>(cur, cmask, Vi, Vl);
       }
-      if (qload && leave) {
+      if (qload && leave && !(GP_EXP_SKIP_ACC && yin > g.y_begin + 4)) {
         typename Acc::Raw cur;
         acc.stage_read(stage_in, 2 * par + 1, cur, t);
         if (cmask == 0xfu) acc.template accum<-1, true>(cur, cmask, Vi, Vl);
@@ -275,7 +281,7 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
     } else {
       // the entering and the leaving coefficient row of this march row sit in slot `tring.s` of the TMA ring (auxiliary warp 0)
       mbar_wait_park(bars + GPB_TFULL + tring.s, tring.ph);
-      if (qload && (enter || leave)) {
+      if (qload && (enter || leave) && !(GP_EXP_SKIP_ACC && yin > g.y_begin + 4)) {
         const int4* slot = reinterpret_cast<const int4*>(stage_in) + ((size_t)tring.s * 2 * GP_NT + (t - tA)) * P::NP;
         acc.accum_staged(slot, slot + (size_t)GP_NT * P::NP, gx >> 2, enter, leave, cmask, Vl);
       }
@@ -450,14 +456,9 @@ __device__ __forceinline__ void gp_solve(const GfCommon& gc, const GfGeom& gg, u
   sol.init(gc, blockIdx.z, reinterpret_cast<typename P::Shared*>(smem + L::off_sh), gg);
   if (act) sol.row_prefetch(g.ys, gx);
   GpRing ring;
-  for (int yo = g.ys; yo < g.ye; ++yo) {
-    mbar_wait_park(bars + GPB_READY + ring.s, ring.ph);
-    uint32_t si[2][NIa];
-    double sd[2][ND];
-    if (act) gp_window_pair<P>(gp_stage<P>(smem, ring.s), g, tq, h, si, sd);
-    mbar_arrive(bars + GPB_EMPTY + ring.s);   // everything this thread needs of the stage is in registers
-    ring.template next<NSTAGE>();
-    if (act) {
+  // the per-pixel work of output row yo from its window sums
+  auto work = [&](int yo, uint32_t (&si)[2][NIa], double (&sd)[2][ND]) {
+    if (act && !(GP_EXP_SKIP_SOLVE && yo > g.ys)) {
       sol.row_pickup();
       if (yo + 1 < g.ye) sol.row_prefetch(yo + 1, gx);
       const int ny = min(yo + g.r, g.H - 1) - max(yo - g.r, 0) + 1;
@@ -466,6 +467,17 @@ __device__ __forceinline__ void gp_solve(const GfCommon& gc, const GfGeom& gg, u
       sol.column(0, yo, gx, ny * nx0, si[0], sd[0], true);
       sol.column(1, yo, gx + 1, ny * nx1, si[1], sd[1], second);
       sol.store_pair(yo, gx, second);
+    }
+  };
+  {
+    for (int yo = g.ys; yo < g.ye; ++yo) {
+      mbar_wait_park(bars + GPB_READY + ring.s, ring.ph);
+      uint32_t si[2][NIa];
+      double sd[2][ND];
+      if (act) gp_window_pair<P>(gp_stage<P>(smem, ring.s), g, tq, h, si, sd);
+      mbar_arrive(bars + GPB_EMPTY + ring.s);   // everything this thread needs of the stage is in registers
+      ring.template next<NSTAGE>();
+      work(yo, si, sd);
     }
   }
   sol.finish();
