@@ -101,6 +101,11 @@ int uwip_channel_stretch_u8(uwip_ctx* ctx, const uint8_t* src, size_t src_pitch,
                             int* high_bin);
 int uwip_channel_stretch_u8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int width,
                                 int height, int lo, int hi);
+/* the same for PITCHED device planes - what cv::cuda::GpuMat holds (cudaMallocPitch), i.e. the arguments of
+ * imgChannelStretchGPU (preprocessing.cpp:109-144); stream ordered, does not synchronise */
+int uwip_channel_stretch_u8_dev_pitched(uwip_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
+                                        uint8_t* d_dst, size_t dst_pitch, int width, int height, int lo,
+                                        int hi);
 
 /* ---- modules/histretch/src/histretch.cpp:219-254 (the -c=<letters> channel loop) ------------ */
 /* channels: ordered letters; every letter of the CLI is built - RGB, HSV, HLS ('hsl'), Lab ('Lab') and

@@ -6,9 +6,8 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "pipe": ["-DGP_GF1A_ACC_REGS=152"],
-    "nopipe": ["-DGP_GF1A_ACC_REGS=152", "-DGP_PIPE_A=0", "-DGP_PIPE_B=0"],
-    "pipe_a104": ["-DGP_GF1A_ACC_REGS=152", "-DGP_GF2A_ACC_REGS=104"],
+    "one": [],
+    "one_a160": ["-DGP_GF1A_ACC_REGS=160", "-DGP_GF2A_ACC_REGS=136"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 
@@ -37,5 +36,42 @@ def run():
         except Exception as e:
             print(name, "FAILED", r.stderr[-500:], flush=True)
 
+def trace():
+    """One chain pass with the trace build; prints per-role clock stamps (cycles, relative) of 64 rows of one CTA."""
+    os.environ["UWIP_LIB"] = os.path.join(OUT, "libuwip_trace.so")
+    import ctypes
+    import numpy as np
+    import torch
+    import uwimageproc_b200 as u
+    ctx = u.Context(0)
+    n, W, H = 86, 3840, 2160
+    d_in = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty_like(d_in)
+    ctx.synth_dev(d_in, 0x5EED0004, 0, n, W, H)
+    for _ in range(2):
+        ctx.chain_dev(d_in, d_out, n, W, H)
+    ctx.synchronize()
+    buf = np.zeros((4, 64, 12), np.int64)
+    rc = ctx.lib.uwip_exp_trace(ctypes.c_void_p(buf.ctypes.data))
+    assert rc == 0, rc
+    names = ["gf1a", "gf1b", "gf2a", "gf2b"]
+    ev = ["acc_done", "acc_gotEMPTY", "acc_published", "aux_gotFULL", "aux_scanned", "sol_gotREADY", "sol_loaded", "sol_done"]
+    for k in range(4):
+        t0 = buf[k, 0, 0]
+        print("==", names[k], " (cycles relative to acc_done of row 600)")
+        print("row " + " ".join("%13s" % e for e in ev))
+        for r in list(range(0, 12)) + [63]:
+            print("%3d " % r + " ".join("%13d" % (buf[k, r, e] - t0) for e in range(8)))
+        d = buf[k]
+        per_row = (buf[k, 63, :8] - buf[k, 0, :8]) / 63.0
+        print("cycles/row per event:", " ".join("%.0f" % v for v in per_row))
+        d = buf[k]
+        print("ACC inside: top->inputs ready %.0f  inputs->entering row done %.0f  leaving row %.0f   (a-kernels: cp.async wait / enter / leave; b: TMA wait / both rows / -)" % (
+            (d[:, 9] - d[:, 8]).mean(), (d[:, 10] - d[:, 9]).mean() if k in (0, 2) else (d[:, 0] - d[:, 9]).mean(), (d[:, 0] - d[:, 10]).mean() if k in (0, 2) else 0.0))
+        print("means: acc wait EMPTY %.0f  acc publish %.0f  aux scan %.0f  FULL->auxwake %.0f  READY->solwake %.0f  sol load %.0f  sol math %.0f" % (
+            (d[:, 1] - d[:, 0]).mean(), (d[:, 2] - d[:, 1]).mean(), (d[:, 4] - d[:, 3]).mean(), (d[:, 3] - d[:, 2]).mean(),
+            (d[:, 5] - d[:, 4]).mean(), (d[:, 6] - d[:, 5]).mean(), (d[:, 7] - d[:, 6]).mean()))
+
+
 if __name__ == "__main__":
-    {"build": build, "run": run}[sys.argv[1]]()
+    {"build": build, "run": run, "trace": trace}[sys.argv[1]]()

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("UWIP_LIB") or os.path.join(HERE, "libuwip.so")  # UWIP_LIB: a build variant under test (scratch/variants.py)
+LIB_PATH = os.path.join(HERE, "libuwip.so")
 
 UWIP_OK = 0
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "uwip_histogram_u8_dev": (_i, [_P, _u8p, _i, _i, _P]),
     "uwip_channel_stretch_u8": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "uwip_channel_stretch_u8_dev": (_i, [_P, _u8p, _u8p, _i, _i, _i, _i]),
+    "uwip_channel_stretch_u8_dev_pitched": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i, _i, _i]),
     "uwip_histretch_bgr8": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i, C.c_char_p, _i, _i, _i, _i]),
     "uwip_histretch_bgr8_dev": (_i, [_P, _u8p, _u8p, _i, _i, _i, C.c_char_p, _i, _i, _i, _i]),
     "uwip_clahe_u8": (_i, [_P, _u8p, _sz, _u8p, _sz, _i, _i, _d, _i, _i]),
@@ -94,10 +95,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UWIP_LIB") or LIB_PATH   # UWIP_LIB: a build variant under test (scratch/variants.py)
+    if not os.path.exists(path):
         raise UwipError(-2, "libuwip.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(nvcc, sm_100a).  There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res

@@ -294,6 +294,21 @@ int uwip_channel_stretch_u8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_
   return k_apply_lut_plane(ctx, d_src, d_dst, 1, (size_t)w * h, dl);
 }
 
+// pitched device planes (cv::cuda::GpuMat allocates with cudaMallocPitch: a 1920-wide plane has step 2048): the rows are
+// gathered into the contiguous workspace, stretched there and scattered back, all on the context's stream
+int uwip_channel_stretch_u8_dev_pitched(uwip_ctx* ctx, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, int w, int h,
+                                        int lo, int hi) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, d_src && d_dst && w > 0 && h > 0 && src_pitch >= (size_t)w && dst_pitch >= (size_t)w, "bad argument");
+  if (src_pitch == (size_t)w && dst_pitch == (size_t)w) return uwip_channel_stretch_u8_dev(ctx, d_src, d_dst, w, h, lo, hi);
+  uint8_t* tmp = (uint8_t*)uwip_slot(ctx, SLOT_STAGE_IN, (size_t)w * h);
+  if (!tmp) return UWIP_ERR_NOMEM;
+  UWIP_CUDA(ctx, cudaMemcpy2DAsync(tmp, (size_t)w, d_src, src_pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, ctx->stream));
+  UWIP_CHECK(uwip_channel_stretch_u8_dev(ctx, tmp, tmp, w, h, lo, hi));
+  UWIP_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dst_pitch, tmp, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, ctx->stream));
+  return UWIP_OK;
+}
+
 int uwip_channel_stretch_u8(uwip_ctx* ctx, const uint8_t* src, size_t sp, uint8_t* dst, size_t dp, int w, int h, int lo, int hi,
                             int* low_bin, int* high_bin) {
   CTX_GUARD(ctx);

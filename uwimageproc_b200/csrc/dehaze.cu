@@ -1077,3 +1077,9 @@ int guided_filter_u8_dev(uwip_ctx* ctx, const uint8_t* d_guide, const double* d_
   UWIP_CHECK(gp_launch<PipGFq>(ctx, "gfq_out", FUNC_GFQ, gc, 1, W, H, r));
   return UWIP_OK;
 }
+
+#if GP_TRACE
+extern "C" int uwip_exp_trace(long long* out) {   // timing-experiment builds only (scratch/variants.py)
+  return (int)cudaMemcpyFromSymbol(out, gp_trace_buf, sizeof(gp_trace_buf));
+}
+#endif

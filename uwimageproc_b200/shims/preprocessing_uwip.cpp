@@ -1,10 +1,12 @@
 // preprocessing_uwip.cpp - modules/common/preprocessing.cpp re-implemented on the C ABI of libuwip.so.
 // Same names, argument meaning and in-place behaviour as the reference (file:line cited per function);
 // no pixel arithmetic happens on the host and there is no CPU fallback: when libuwip cannot create a
-// context (no sm_100 device) every call records the error and leaves its outputs untouched.
+// context (no sm_100 device) or a call fails, the error is printed and the process aborts; with
+// UWIP_SHIM_SOFT_ERRORS=1 the call records the error and leaves its outputs untouched instead.
 #include "preprocessing.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -27,15 +29,22 @@ uwip_ctx* shim_ctx() {
       g_shim.err = uwip_last_error(nullptr);
       std::fprintf(stderr, "uwip shim: %s\n", g_shim.err.c_str());
       g_shim.ctx = nullptr;
+      const char* soft = std::getenv("UWIP_SHIM_SOFT_ERRORS");
+      if (!(soft && soft[0] == '1')) std::abort();
     }
   }
   return g_shim.ctx;
 }
+// The reference functions are void: a failure cannot be returned.  It is LOUD by default - the message goes to stderr and the
+// process aborts (a frame silently left unstretched is worse than a crash) - unless UWIP_SHIM_SOFT_ERRORS=1 asks for the
+// "print and continue" behaviour of the reference (histretch.cpp:252); the status stays readable through uwipShimLastStatus().
 void shim_done(int rc) {
   g_shim.status = rc;
   if (rc != UWIP_OK) {
-    g_shim.err = uwip_last_error(g_shim.ctx);
+    g_shim.err = g_shim.ctx ? uwip_last_error(g_shim.ctx) : "no usable CUDA device (libuwip has no CPU fallback)";
     std::fprintf(stderr, "uwip shim: %s\n", g_shim.err.c_str());
+    const char* soft = std::getenv("UWIP_SHIM_SOFT_ERRORS");
+    if (!(soft && soft[0] == '1')) std::abort();
   }
 }
 bool is_u8_plane(const cv::Mat& m) { return !m.empty() && m.type() == CV_8UC1; }
@@ -72,11 +81,13 @@ void imgChannelStretch(cv::Mat imgOriginal, cv::Mat imgStretched, int lowerPerce
 void imgChannelStretchGPU(cv::cuda::GpuMat imgOriginal, cv::cuda::GpuMat imgStretched, int lowerPercentile, int higherPercentile) {
   uwip_ctx* ctx = shim_ctx();
   if (!ctx) return;
-  if (imgOriginal.rows != imgStretched.rows || imgOriginal.cols != imgStretched.cols || !imgOriginal.isContinuous() || !imgStretched.isContinuous()) {
-    shim_done(UWIP_ERR_INVALID);  // the _dev entry points take contiguous rows
+  if (imgOriginal.rows != imgStretched.rows || imgOriginal.cols != imgStretched.cols) {
+    shim_done(UWIP_ERR_INVALID);  // preprocessing.h:60-64: same dimensions required
     return;
   }
-  int rc = uwip_channel_stretch_u8_dev(ctx, imgOriginal.data, imgStretched.data, imgOriginal.cols, imgOriginal.rows, lowerPercentile, higherPercentile);
+  // GpuMat planes are pitched (cudaMallocPitch): the pitched entry point takes them as they are
+  int rc = uwip_channel_stretch_u8_dev_pitched(ctx, imgOriginal.data, (size_t)imgOriginal.step, imgStretched.data, (size_t)imgStretched.step,
+                                               imgOriginal.cols, imgOriginal.rows, lowerPercentile, higherPercentile);
   if (rc == UWIP_OK) rc = uwip_synchronize(ctx);  // cv::cuda::add / multiply of the reference block too
   shim_done(rc);
 }
