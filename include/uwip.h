@@ -230,6 +230,21 @@ int uwip_calc_blur_bgr8(uwip_ctx* ctx, const uint8_t* src, size_t pitch, int wid
 int uwip_calc_blur_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, int n_frames, int width, int height,
                             int aperture, double* d_mean_std);
 
+/* ---- JPEG files to and from the device ------------------------------------ */
+/* imread / imwrite around the chain (histretch.cpp:158,268, aclahe.cpp:135, bgdehaze/main.py:16,19) for baseline JPEG
+ * files: nvJPEG decodes into the bgr8 device layout the chain reads and encodes from the one it writes, so a frame crosses
+ * PCIe as its compressed bytes only.  The decoded pixels are nvJPEG's (its IDCT is not bit-identical to libjpeg-turbo's:
+ * a few levels from cv2.imread, mostly the 4:2:0 chroma upsampling: max 4, mean 0.6 on the test frame); encoding is 4:2:0 at `quality` (cv2.imwrite's default is 95). */
+int uwip_jpeg_info(uwip_ctx* ctx, const uint8_t* jpeg, size_t len, int* width, int* height);
+int uwip_jpeg_decode_bgr8_dev(uwip_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* d_bgr, int width,
+                              int height);
+/* out == NULL: only *out_len (the size of the stream) is returned */
+int uwip_jpeg_encode_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_bgr, int width, int height, int quality,
+                              uint8_t* out, size_t cap, size_t* out_len);
+/* JPEG in -> histretch -> aclahe -> bgdehaze on the device -> JPEG out */
+int uwip_chain_jpeg(uwip_ctx* ctx, const uint8_t* jpeg_in, size_t len_in, const uwip_chain_params* p,
+                    int quality, uint8_t* jpeg_out, size_t cap, size_t* len_out);
+
 /* ---- synthetic input + checksums ------------------------------------------------- */
 /* frames first_frame .. first_frame+n_frames-1 of the integer-only generator (twin of
  * oracle/uwip_oracle.py:synth_frame) written to device memory. */

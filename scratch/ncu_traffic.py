@@ -4,8 +4,8 @@ import csv, json, subprocess, sys
 
 rep, n, W, H, out_json, out_md = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], sys.argv[6]
 TAGS = [("hist_frame_kernel", "hist_frame"), ("tilehist_kernel", "clahe_tilehist"), ("clahe_apply_kernel", "clahe_apply"),
-        ("window15_kernel", "dz_window"), ("PolGF1a", "dz_gf1a"), ("PolGF1b", "dz_gf1b"), ("exposure_minmax_kernel", "dz_exposure_minmax"),
-        ("splane_kernel", "dz_splane"), ("PolGF2a", "dz_gf2a"), ("PolGF2b", "dz_gf2b"), ("final_kernel", "dz_final")]
+        ("window15_kernel", "dz_window"), ("PipGF1a", "dz_gf1a"), ("PipGF1b", "dz_gf1b"), ("exposure_minmax_kernel", "dz_exposure_minmax"),
+        ("splane_kernel", "dz_splane"), ("PipGF2a", "dz_gf2a"), ("PipGF2b", "dz_gf2b"), ("final_kernel", "dz_final")]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]

@@ -304,3 +304,34 @@ def test_python_cli_shims(tmp_path, capsys):
     d_dst = str(tmp_path / "res" / "dehazed.png")
     assert CB.main(["--src", src, "--dest", d_dst, "-w", "15"]) == 0
     assert np.abs(cv2.imread(d_dst).astype(int) - O.bgdehaze_frame(fr, 15)[1].astype(int)).max() <= 1
+
+
+# ---- JPEG files to and from the device ----------------------------------------------------------
+def test_jpeg_device_io(ctx):
+    """nvJPEG decode -> chain -> nvJPEG encode without the pixels touching the host.  nvJPEG's IDCT is not libjpeg-turbo's:
+    the decoded pixels are compared with cv2.imdecode (max 4 levels apart on this frame, chroma upsampling differs: bounded here by
+    8 levels and a mean of 1); the chain is then checked against the oracle on the
+    pixels nvJPEG produced, and the encoded result by decoding it again."""
+    cv2 = pytest.importorskip("cv2")
+    fr = O.synth_frame(0x5EED0004, 2, 640, 360)
+    ok, enc = cv2.imencode(".jpg", fr, [cv2.IMWRITE_JPEG_QUALITY, 95])
+    assert ok
+    data = enc.tobytes()
+    assert ctx.jpeg_info(data) == (640, 360)
+    d = ctx.jpeg_decode_dev(data)
+    dec = d.cpu().numpy()
+    ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    diff = np.abs(dec.astype(int) - ref.astype(int))
+    assert diff.max() <= 8 and diff.mean() < 1.0, (diff.max(), diff.mean())
+    out_jpeg = ctx.chain_jpeg(data, quality=95)
+    got = cv2.imdecode(np.frombuffer(out_jpeg, np.uint8), cv2.IMREAD_COLOR)
+    assert got.shape == fr.shape
+    want = O.chain_frame(dec)                      # the oracle on nvJPEG's pixels
+    direct = ctx.chain(dec)                        # the chain on the same pixels, no JPEG on the way out
+    assert np.abs(direct.astype(int) - want.astype(int)).max() <= 1
+    mse = np.mean((got.astype(float) - direct.astype(float)) ** 2)
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-9))
+    assert psnr > 30.0, psnr                       # quality-95 4:2:0 JPEG of the result
+    rt = ctx.jpeg_encode_dev(d, 640, 360, 95)
+    back = cv2.imdecode(np.frombuffer(rt, np.uint8), cv2.IMREAD_COLOR)
+    assert 10 * np.log10(255.0 ** 2 / np.mean((back.astype(float) - dec.astype(float)) ** 2)) > 30.0

@@ -81,6 +81,10 @@ SIGNATURES = {
     "uwip_chain_bgr8_dev": (_i, [_P, _u8p, _u8p, _i, _i, _i, C.POINTER(ChainParams)]),
     "uwip_chain_bgr8": (_i, [_P, _u8p, _u8p, _i, _i, _i, C.POINTER(ChainParams)]),
     "uwip_last_frame_flags": (_i, [_P, _i, _P]),
+    "uwip_jpeg_info": (_i, [_P, _u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "uwip_jpeg_decode_bgr8_dev": (_i, [_P, _u8p, _sz, _u8p, _i, _i]),
+    "uwip_jpeg_encode_bgr8_dev": (_i, [_P, _u8p, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
+    "uwip_chain_jpeg": (_i, [_P, _u8p, _sz, C.POINTER(ChainParams), _i, _u8p, _sz, C.POINTER(_sz)]),
     "uwip_calc_blur_bgr8": (_i, [_P, _u8p, _sz, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(_d), _u8p, _sz]),
     "uwip_calc_blur_bgr8_dev": (_i, [_P, _u8p, _i, _i, _i, _i, _P]),
     "uwip_synth_bgr8_dev": (_i, [_P, _u8p, C.c_uint32, _i, _i, _i, _i]),

@@ -247,6 +247,43 @@ class Context:
         p = params or self.chain_params()
         self._ck(self.lib.uwip_chain_bgr8_dev(self.h, _ptr(d_src), _ptr(d_dst), n, width, height, C.byref(p)))
 
+    # ---- JPEG files to and from the device (nvJPEG) ------------------------------------------------
+    def jpeg_info(self, data):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.uwip_jpeg_info(self.h, _ptr(buf), buf.size, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def jpeg_decode_dev(self, data, d_bgr=None):
+        """JPEG bytes -> bgr8 frame on the device (torch uint8 tensor H x W x 3 unless one is passed in)."""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        w, h = self.jpeg_info(data)
+        if d_bgr is None:
+            import torch
+
+            d_bgr = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+        self._ck(self.lib.uwip_jpeg_decode_bgr8_dev(self.h, _ptr(buf), buf.size, _ptr(d_bgr), w, h))
+        self.synchronize()
+        return d_bgr
+
+    def jpeg_encode_dev(self, d_bgr, width, height, quality=95):
+        n = C.c_size_t()
+        cap = width * height * 3 + 65536
+        out = np.empty(cap, np.uint8)
+        self._ck(self.lib.uwip_jpeg_encode_bgr8_dev(self.h, _ptr(d_bgr), width, height, int(quality), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def chain_jpeg(self, data, params=None, quality=95):
+        """JPEG bytes in -> chain on the device -> JPEG bytes out."""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        w, h = self.jpeg_info(data)
+        p = params or self.chain_params()
+        n = C.c_size_t()
+        cap = w * h * 3 + 65536
+        out = np.empty(cap, np.uint8)
+        self._ck(self.lib.uwip_chain_jpeg(self.h, _ptr(buf), buf.size, C.byref(p), int(quality), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].tobytes()
+
     def last_frame_flags(self, n):
         """Per-frame status of the last batched chain / bgdehaze call: 1 = the reference output is NaN (D9)."""
         out = np.empty(n, np.int32)

@@ -127,6 +127,7 @@ void uwip_destroy(uwip_ctx* ctx) {
   for (auto& r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (int i = 0; i < uwip_ctx::kSlots; i++)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+  jpeg_io_destroy(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -730,6 +731,44 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   if (e != cudaSuccess) { uwip_set_err(ctx, "chain pipeline: %s", cudaGetErrorString(e)); return UWIP_ERR_CUDA; }
   return UWIP_OK;
+}
+
+// ---- JPEG files to and from the device ---------------------------------------------------------
+int uwip_jpeg_info(uwip_ctx* ctx, const uint8_t* jpeg, size_t len, int* width, int* height) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, jpeg && len > 0 && width && height, "bad argument");
+  return jpeg_info(ctx, jpeg, len, width, height);
+}
+int uwip_jpeg_decode_bgr8_dev(uwip_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* d_bgr, int width, int height) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, jpeg && len > 0 && d_bgr && width > 0 && height > 0, "bad argument");
+  int w = 0, h = 0;
+  UWIP_CHECK(jpeg_info(ctx, jpeg, len, &w, &h));
+  UWIP_REQUIRE(ctx, w == width && h == height, "the JPEG stream has another size (uwip_jpeg_info)");
+  return jpeg_decode_dev(ctx, jpeg, len, d_bgr, w, h);
+}
+int uwip_jpeg_encode_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_bgr, int width, int height, int quality, uint8_t* out, size_t cap, size_t* out_len) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, d_bgr && width > 0 && height > 0 && out_len && quality >= 1 && quality <= 100, "bad argument");
+  return jpeg_encode_dev(ctx, d_bgr, width, height, quality, out, cap, out_len);
+}
+// JPEG in -> histretch -> aclahe -> bgdehaze on the device -> JPEG out: the file never exists as pixels on the host
+int uwip_chain_jpeg(uwip_ctx* ctx, const uint8_t* jpeg_in, size_t len_in, const uwip_chain_params* p, int quality, uint8_t* jpeg_out,
+                    size_t cap, size_t* len_out) {
+  CTX_GUARD(ctx);
+  UWIP_REQUIRE(ctx, jpeg_in && len_in > 0 && len_out, "bad argument");
+  int w = 0, h = 0;
+  UWIP_CHECK(jpeg_info(ctx, jpeg_in, len_in, &w, &h));
+  UWIP_CHECK(chain_check(ctx, p, 1, w, h));
+  const size_t fbytes = (size_t)w * h * 3;
+  uint8_t* d_in = (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_IN0, fbytes);
+  uint8_t* d_out = (uint8_t*)uwip_slot(ctx, SLOT_CHAIN_OUT0, fbytes);
+  FrameState* fs = frame_state_get(ctx, 1);
+  int32_t* flags = flags_get(ctx, 1);
+  if (!d_in || !d_out || !fs || !flags) return UWIP_ERR_NOMEM;
+  UWIP_CHECK(jpeg_decode_dev(ctx, jpeg_in, len_in, d_in, w, h));
+  UWIP_CHECK(chain_sub(ctx, d_in, d_out, 1, w, h, *p, fs, flags));
+  return jpeg_encode_dev(ctx, d_out, w, h, quality, jpeg_out, cap, len_out);
 }
 
 int uwip_last_frame_flags(uwip_ctx* ctx, int n, int32_t* flags_host) {

@@ -39,6 +39,7 @@ struct uwip_ctx {
   int flags_n = 0;         // frames covered by SLOT_FLAGS (last batched chain / dehaze call)
   // opt-in dynamic shared memory already granted on THIS context's device, per kernel (cudaFuncSetAttribute is
   // per device: a process-global flag would leave the second device of a process without the opt-in)
+  void* jpeg = nullptr;    // nvJPEG handles of the file entry points (jpegio.cu), created on first use
   static const int kFuncs = 16;
   size_t func_smem[kFuncs] = {};
 };
@@ -384,6 +385,12 @@ int dehaze_wave_frames(const uwip_ctx* ctx, int w);  // frames whose guided-filt
 FrameState* frame_state_get(uwip_ctx* ctx, int n);
 int boxfilter_f64_dev(uwip_ctx* ctx, const double* d_src, double* d_tmp, double* d_dst, int w, int h, int r);
 int guided_filter_u8_dev(uwip_ctx* ctx, const uint8_t* d_guide, const double* d_p, double* d_q, int w, int h, int range, int r, double eps, FrameState* fs);
+
+// jpegio.cu
+int jpeg_info(uwip_ctx* ctx, const uint8_t* data, size_t len, int* w, int* h);
+int jpeg_decode_dev(uwip_ctx* ctx, const uint8_t* data, size_t len, uint8_t* d_bgr, int w, int h);
+int jpeg_encode_dev(uwip_ctx* ctx, const uint8_t* d_bgr, int w, int h, int quality, uint8_t* out, size_t cap, size_t* out_len);
+void jpeg_io_destroy(uwip_ctx* ctx);
 
 // synth.cu
 int synth_frames_dev(uwip_ctx* ctx, uint8_t* d_dst, uint32_t seed, int first, int n, int w, int h);
