@@ -260,33 +260,77 @@ __global__ void __launch_bounds__(WK_THREADS) window_kernel(const uint8_t* __res
 }
 
 // ---- fast path: both windows 15x15 (the reference's only reachable configuration unless -w is given) ----
-// Tile 64 x 32 outputs, 256 threads, three CTAs per SM (64 x 48 at two CTAs per SM measured 8 % slower).  The window max / min of a run of outputs is formed in registers by
-// doubling: m2[i] = op(p[i], p[i+1]), m4[i] = op(m2[i], m2[i+2]), m8[i] = op(m4[i], m4[i+4]),
-// m15[i] = op(m8[i], m8[i+7])  (4 ops per output instead of 14), on 16-bit pairs (VIMNMX.U16x2).
+// Tile 64 x 32 outputs, 256 threads, three CTAs per SM.  The window max / min of a run of outputs is formed in registers on
+// 16-bit pairs with the three-input VIMNMX3.U16x2:  m3[i] = op(p[i], p[i+1], p[i+2]),  m9[i] = op(m3[i], m3[i+3], m3[i+6]),
+// m15[i] = op(m9[i], m9[i+6])  - 3 + 18/N instructions per output of a run of N instead of 14.
+// The arg-min of D is found in two steps: every pixel only feeds the packed integer differences (max_R - max_B,
+// max_R - max_G; two instructions), and the fp64 value of BGDehaze.py:20-21 is evaluated for the pixels that reach the
+// tile's integer minimum (one unit of the integer difference is 1/range, the fp64 rounding is far below that, so the fp64
+// minimum is always among them).
 constexpr int WF_TX = 64, WF_TY = 32, WF_R = 7, WF_RH = WF_TY + 2 * WF_R;   // region rows
 constexpr int WF_VR = WF_TY / 4, WF_CTAS = 3;  // output rows per vertical run (four runs of 64 columns); CTAs per SM
-constexpr int WF_PP = 84;   // region pitch in words: 78 used; 21 x 16 bytes (odd) -> conflict-free 16-byte loads down a column of rows
+constexpr int WF_RB = 8;    // region column c is image column x0 - WF_RB + c (80 columns: the 240 bytes of a row start on a word)
+constexpr int WF_PP = 84;   // region pitch in words: 80 used; 21 x 16 bytes (odd) -> conflict-free 16-byte loads down a column of rows
 constexpr int WF_HP = 68;   // pitch of the horizontal results: 17 x 16 bytes
+constexpr int WF_HN = 16;   // outputs per horizontal task
 
-template <int N, bool MAX>
-__device__ __forceinline__ void win15(const uint32_t (&p)[N + 14], uint32_t (&o)[N]) {
-  uint32_t a[N + 13], b[N + 11], c[N + 7];
+template <int N, bool MAX, int OFF, int M>
+__device__ __forceinline__ void win15(const uint32_t (&p)[M], uint32_t (&o)[N]) {
+  static_assert(OFF + N + 14 <= M, "window run");
+  uint32_t a[N + 12], b[N + 6];
 #pragma unroll
-  for (int i = 0; i < N + 13; i++) a[i] = MAX ? __vmaxu2(p[i], p[i + 1]) : __vminu2(p[i], p[i + 1]);
+  for (int i = 0; i < N + 12; i++)
+    a[i] = MAX ? __vimax3_u16x2(p[OFF + i], p[OFF + i + 1], p[OFF + i + 2]) : __vimin3_u16x2(p[OFF + i], p[OFF + i + 1], p[OFF + i + 2]);
 #pragma unroll
-  for (int i = 0; i < N + 11; i++) b[i] = MAX ? __vmaxu2(a[i], a[i + 2]) : __vminu2(a[i], a[i + 2]);
+  for (int i = 0; i < N + 6; i++) b[i] = MAX ? __vimax3_u16x2(a[i], a[i + 3], a[i + 6]) : __vimin3_u16x2(a[i], a[i + 3], a[i + 6]);
 #pragma unroll
-  for (int i = 0; i < N + 7; i++) c[i] = MAX ? __vmaxu2(b[i], b[i + 4]) : __vminu2(b[i], b[i + 4]);
-#pragma unroll
-  for (int i = 0; i < N; i++) o[i] = MAX ? __vmaxu2(c[i], c[i + 7]) : __vminu2(c[i], c[i + 7]);
+  for (int i = 0; i < N; i++) o[i] = MAX ? __vmaxu2(b[i], b[i + 6]) : __vminu2(b[i], b[i + 6]);
 }
 
-// candidate for the arg-min of D: exact integer difference first (it decides whenever it differs: one
-// unit is 1/range, the fp64 rounding of BGDehaze.py:20-21 is far below that), then the reference's
-// fp64 value, then the flat index
-struct ArgCand { int di; double d; unsigned idx; };
-__device__ __forceinline__ bool cand_less(int ai, double ad, unsigned aidx, int bi, double bd, unsigned bidx) {
-  return (ai < bi) || (ai == bi && ((ad < bd) || (ad == bd && aidx < bidx)));
+__device__ __forceinline__ void wf_cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+// rows of one vertical run: packs (B', G', R', min_B') and min_G' of every pixel (main.py:17's k' = k - kmin) and returns the
+// packed minimum of the biased integer differences (low half max_R - max_B + 256, high half max_R - max_G + 256).
+// FAST: all WF_VR rows lie inside the image and no window touches the border
+template <bool FAST>
+__device__ __forceinline__ uint32_t wf_emit_rows(const uint32_t (&mx0)[WF_VR], const uint32_t (&mx1)[WF_VR], const uint32_t (&mn0)[WF_VR],
+                                                 const uint32_t* __restrict__ pc0, const uint32_t* __restrict__ pc1,
+                                                 uint32_t* __restrict__ kqp, uint8_t* __restrict__ mgq, unsigned Wp, int nrows, int gy0, int H,
+                                                 bool xt, bool inside, uint32_t km2) {
+  uint32_t dmin2 = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < WF_VR; i++) {
+    if (!FAST && i >= nrows) break;
+    const unsigned o = (unsigned)i * Wp;
+    if (!FAST && !inside) { kqp[o] = 0u; mgq[o] = 0; continue; }
+    const uint32_t t0 = pc0[i * WF_PP] - km2, t1 = pc1[i * WF_PP] - km2;   // (B', G'), (R', R')
+    uint32_t tn = mn0[i] - km2;                                            // (min_B', min_G')
+    if (!FAST) {
+      const int gy = gy0 + i;
+      if (xt || gy < WF_R || gy + WF_R >= H) tn = 0u;                       // the reference's min filter pads with 0 (BGDehaze.py:32)
+    }
+    kqp[o] = __byte_perm(__byte_perm(t0, t1, 0x4420), tn, 0x4210);          // B' | G' << 8 | R' << 16 | min_B' << 24
+    mgq[o] = (uint8_t)(tn >> 16);
+    dmin2 = __vminu2(dmin2, mx1[i] + 0x01000100u - mx0[i]);                 // D (BGDehaze.py:20-21) in units of 1/range
+  }
+  return dmin2;
+}
+
+// exact D of the pixels of a run whose integer difference is the tile's minimum: first index of the smallest fp64 value
+template <int CH>
+__device__ __forceinline__ void wf_exact(const uint32_t (&mx0)[WF_VR], const uint32_t (&mx1)[WF_VR], int nrows, uint32_t target, int kmin,
+                                         const double* s_nrm, unsigned idx0, unsigned W, double& bd, unsigned& bi) {
+#pragma unroll
+  for (int i = 0; i < WF_VR; i++) {
+    if (i >= nrows) break;
+    const uint32_t mr = mx1[i] & 0xffffu, mc = CH ? (mx0[i] >> 16) : (mx0[i] & 0xffffu);
+    if (mr + 256u - mc == target) {
+      const double d = s_nrm[mr - kmin] - s_nrm[mc - kmin];
+      if (d < bd) { bd = d; bi = idx0 + (unsigned)i * W; }   // rows go down: the index only grows
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* __restrict__ src, int W, int H, int Wp,
@@ -294,25 +338,53 @@ __global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* _
                                                           uint8_t* __restrict__ mgp, ArgPartial* __restrict__ partials) {
   extern __shared__ __align__(16) uint32_t s_w[];
   __shared__ double s_nrm[256];
-  __shared__ ArgPartial s_part[8];
+  __shared__ uint32_t s_wmin[8];
+  __shared__ int s_cnt[2];
   uint32_t* P0 = s_w;                       // [WF_RH][84] (B | G<<16), replicate border
-  uint32_t* P1 = P0 + WF_RH * WF_PP;        // [WF_RH][84] R
+  uint32_t* P1 = P0 + WF_RH * WF_PP;        // [WF_RH][84] (R | R<<16)
   uint32_t* HX0 = P1 + WF_RH * WF_PP;       // [WF_RH][68] horizontal max (B,G)
-  uint32_t* HX1 = HX0 + WF_RH * WF_HP;      // horizontal max R
+  uint32_t* HX1 = HX0 + WF_RH * WF_HP;      // horizontal max (R,R)
   uint32_t* HN0 = HX1 + WF_RH * WF_HP;      // horizontal min (B,G)
-  const int f = blockIdx.z, tid = threadIdx.x;
+  const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t* img = src + (size_t)f * W * H * 3;
   const int x0 = blockIdx.x * WF_TX, y0 = blockIdx.y * WF_TY;
   const int kmin = fs[f].kmin, range = (int)fs[f].kmax - kmin;
   s_nrm[tid] = (double)tid / (double)range;  // normI value of k' (main.py:17)
-  // region [y0-7, y0+WF_TY+7) x [x0-7, x0+73) : WF_RH x 80 pixels (78 used + 2 for the vector loads).
-  // thread = (column, row mod 3); the loads of several rows are issued before the first use
+  if (tid < 2) s_cnt[tid] = 0;
+  // region [y0-7, y0+WF_TY+7) x [x0-8, x0+72): WF_RH x 80 pixels.  The bytes of a region row come in as aligned 32-bit
+  // words into a raw staging area that borrows HX0 (free until the horizontal phase), then get unpacked from shared
+  uint32_t* RAW = HX0;  // [WF_RH][64] words
   const bool words = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);  // rows start on 4-byte boundaries
-  if (words) {
-    // the 240 bytes of a region row come in as aligned 32-bit words (one coalesced request per row instead of 240 byte
-    // loads) into a raw staging area that borrows HX0 (free until the horizontal phase), then get unpacked from shared
-    uint32_t* RAW = HX0;  // [WF_RH][64] words
-    const int xa = max(x0 - WF_R, 0), xb = min(x0 - WF_R + 79, W - 1);  // first / last image column of the region
+  if (words && x0 >= WF_RB && x0 - WF_RB + 80 <= W) {
+    // no column clamp: 60 words per row, a warp per row, then four pixels (three words) per unpack task
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(img + (size_t)(x0 - WF_RB) * 3);
+#pragma unroll
+    for (int k = 0; k < (WF_RH + 7) / 8; k++) {
+      const int ry = warp + 8 * k;
+      if (ry < WF_RH) {
+        const int y = min(max(y0 - WF_R + ry, 0), H - 1);
+        const uint32_t* row = col + (size_t)y * (W * 3 / 4);
+        wf_cp_async4(RAW + ry * 64 + lane, row + lane);
+        if (lane < 28) wf_cp_async4(RAW + ry * 64 + 32 + lane, row + 32 + lane);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int t = tid; t < WF_RH * 20; t += 256) {
+      const int ry = t / 20, g = t - ry * 20;
+      const uint32_t* w = RAW + ry * 64 + 3 * g;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      uint4 bg, rr;
+      bg.x = __byte_perm(w0, 0u, 0x4140); bg.y = __byte_perm(w0, w1, 0x0403) & 0x00ff00ffu;
+      bg.z = __byte_perm(w1, 0u, 0x4342); bg.w = __byte_perm(w2, 0u, 0x4241);
+      rr.x = __byte_perm(w0, 0u, 0x4242); rr.y = __byte_perm(w1, 0u, 0x4141);
+      rr.z = __byte_perm(w2, 0u, 0x4040); rr.w = __byte_perm(w2, 0u, 0x4343);
+      *reinterpret_cast<uint4*>(P0 + ry * WF_PP + 4 * g) = bg;
+      *reinterpret_cast<uint4*>(P1 + ry * WF_PP + 4 * g) = rr;
+    }
+  } else if (words) {
+    // frame's left / right edge: columns clamp (replicate border); bytes picked one by one
+    const int xa = max(x0 - WF_RB, 0), xb = min(x0 - WF_RB + 79, W - 1);  // first / last image column of the region
     const int byte0 = (xa * 3) & ~3;
     const int nw = ((xb * 3 + 2) >> 2) - (byte0 >> 2) + 1;             // <= 61
 #pragma unroll 4
@@ -326,19 +398,19 @@ __global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* _
     __syncthreads();
     if (tid < 240) {
       const int rx = tid % 80, rr = tid / 80;
-      const int xc = min(max(x0 - WF_R + rx, 0), W - 1);
+      const int xc = min(max(x0 - WF_RB + rx, 0), W - 1);
       const uint8_t* rawb = reinterpret_cast<const uint8_t*>(RAW) + (xc * 3 - byte0);
 #pragma unroll 7
       for (int ry = rr; ry < WF_RH; ry += 3) {
         const uint8_t* p = rawb + ry * 256;
         uint32_t b = p[0], g = p[1], r = p[2];
         P0[ry * WF_PP + rx] = b | (g << 16);
-        P1[ry * WF_PP + rx] = r;
+        P1[ry * WF_PP + rx] = r | (r << 16);
       }
     }
   } else if (tid < 240) {
     const int rx = tid % 80, rr = tid / 80;
-    const int xc = min(max(x0 - WF_R + rx, 0), W - 1);
+    const int xc = min(max(x0 - WF_RB + rx, 0), W - 1);
     const uint8_t* col = img + (size_t)xc * 3;
 #pragma unroll 7
     for (int ry = rr; ry < WF_RH; ry += 3) {
@@ -346,119 +418,108 @@ __global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* _
       const uint8_t* p = col + (size_t)y * W * 3;
       uint32_t b = __ldg(p), g = __ldg(p + 1), r = __ldg(p + 2);
       P0[ry * WF_PP + rx] = b | (g << 16);
-      P1[ry * WF_PP + rx] = r;
+      P1[ry * WF_PP + rx] = r | (r << 16);
     }
   }
   __syncthreads();
-  // horizontal: task = (row, run of 8 outputs); consecutive lanes take consecutive rows
-  for (int task = tid; task < WF_RH * 8; task += 256) {
-    int ry = task % WF_RH, j = task / WF_RH;
-    const uint4* r0 = reinterpret_cast<const uint4*>(P0 + ry * WF_PP + 8 * j);
-    const uint4* r1 = reinterpret_cast<const uint4*>(P1 + ry * WF_PP + 8 * j);
-    uint32_t p[22], o[8];
+  // horizontal: task = (row, run of 16 outputs); consecutive lanes take consecutive rows.  Output column o is the window
+  // of region columns o + 1 .. o + 15
+  if (tid < WF_RH * (WF_TX / WF_HN)) {
+    const int ry = tid % WF_RH, j = tid / WF_RH;
+    uint32_t p[WF_HN + 16], o[WF_HN];
+    const uint4* r0 = reinterpret_cast<const uint4*>(P0 + ry * WF_PP + WF_HN * j);
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-      uint4 v = r0[q];
-      if (4 * q < 22) p[4 * q] = v.x;
-      if (4 * q + 1 < 22) p[4 * q + 1] = v.y;
-      if (4 * q + 2 < 22) p[4 * q + 2] = v.z;
-      if (4 * q + 3 < 22) p[4 * q + 3] = v.w;
-    }
-    win15<8, true>(p, o);
-    uint4* h0 = reinterpret_cast<uint4*>(HX0 + ry * WF_HP + 8 * j);
-    h0[0] = make_uint4(o[0], o[1], o[2], o[3]); h0[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    win15<8, false>(p, o);
-    uint4* hn = reinterpret_cast<uint4*>(HN0 + ry * WF_HP + 8 * j);
-    hn[0] = make_uint4(o[0], o[1], o[2], o[3]); hn[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    for (int q = 0; q < (WF_HN + 16) / 4; q++) { const uint4 v = r0[q]; p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w; }
+    win15<WF_HN, true, 1>(p, o);
+    uint4* h0 = reinterpret_cast<uint4*>(HX0 + ry * WF_HP + WF_HN * j);
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-      uint4 v = r1[q];
-      if (4 * q < 22) p[4 * q] = v.x;
-      if (4 * q + 1 < 22) p[4 * q + 1] = v.y;
-      if (4 * q + 2 < 22) p[4 * q + 2] = v.z;
-      if (4 * q + 3 < 22) p[4 * q + 3] = v.w;
-    }
-    win15<8, true>(p, o);
-    uint4* h1 = reinterpret_cast<uint4*>(HX1 + ry * WF_HP + 8 * j);
-    h1[0] = make_uint4(o[0], o[1], o[2], o[3]); h1[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    for (int q = 0; q < WF_HN / 4; q++) h0[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    win15<WF_HN, false, 1>(p, o);
+    uint4* hn = reinterpret_cast<uint4*>(HN0 + ry * WF_HP + WF_HN * j);
+#pragma unroll
+    for (int q = 0; q < WF_HN / 4; q++) hn[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    const uint4* r1 = reinterpret_cast<const uint4*>(P1 + ry * WF_PP + WF_HN * j);
+#pragma unroll
+    for (int q = 0; q < (WF_HN + 16) / 4; q++) { const uint4 v = r1[q]; p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w; }
+    win15<WF_HN, true, 1>(p, o);
+    uint4* h1 = reinterpret_cast<uint4*>(HX1 + ry * WF_HP + WF_HN * j);
+#pragma unroll
+    for (int q = 0; q < WF_HN / 4; q++) h1[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
   }
   __syncthreads();
   // vertical: thread = (column, run of WF_VR output rows)
   const int x = tid & 63, run = tid >> 6;
-  const int gx = x0 + x;
-  ArgCand b0 = {0x7fffffff, 0.0, 0xffffffffu}, b1 = b0;
-  int bp0 = -1, bp1 = -1;  // (max_R, max_X) pair of the current best: the same pair further down can never win (same D, larger index)
-  if (gx < Wp) {
-    uint32_t p[WF_VR + 14], mx0[WF_VR], mx1[WF_VR], mn0[WF_VR];
-    const int ry0 = run * WF_VR;
+  const int gx = x0 + x, ry0 = run * WF_VR, gy0 = y0 + ry0;
+  const int nrows = gx < Wp ? min(WF_VR, H - gy0) : 0;
+  const bool inside = gx < W;
+  uint32_t mx0[WF_VR], mx1[WF_VR], dmin2 = 0xffffffffu;
+  if (nrows > 0) {
+    uint32_t p[WF_VR + 14], mn0[WF_VR];
 #pragma unroll
     for (int i = 0; i < WF_VR + 14; i++) p[i] = HX0[(ry0 + i) * WF_HP + x];
-    win15<WF_VR, true>(p, mx0);
+    win15<WF_VR, true, 0>(p, mx0);
 #pragma unroll
     for (int i = 0; i < WF_VR + 14; i++) p[i] = HX1[(ry0 + i) * WF_HP + x];
-    win15<WF_VR, true>(p, mx1);
+    win15<WF_VR, true, 0>(p, mx1);
 #pragma unroll
     for (int i = 0; i < WF_VR + 14; i++) p[i] = HN0[(ry0 + i) * WF_HP + x];
-    win15<WF_VR, false>(p, mn0);
-    uint32_t* kqf = kq + (size_t)f * Wp * H;
-    uint8_t* mgf = mgp + (size_t)f * Wp * H;
+    win15<WF_VR, false, 0>(p, mn0);
+    const size_t pix0 = (size_t)f * Wp * H + (size_t)gy0 * Wp + gx;
+    const uint32_t* pc0 = P0 + (ry0 + WF_R) * WF_PP + x + WF_RB;
+    const uint32_t* pc1 = P1 + (ry0 + WF_R) * WF_PP + x + WF_RB;
+    const uint32_t km2 = (uint32_t)kmin * 0x10001u;
     const bool xt = (gx < WF_R) || (gx + WF_R >= W);
+    if (!xt && gy0 >= WF_R && gy0 + WF_VR - 1 + WF_R < H)
+      dmin2 = wf_emit_rows<true>(mx0, mx1, mn0, pc0, pc1, kq + pix0, mgp + pix0, (unsigned)Wp, nrows, gy0, H, xt, inside, km2);
+    else
+      dmin2 = wf_emit_rows<false>(mx0, mx1, mn0, pc0, pc1, kq + pix0, mgp + pix0, (unsigned)Wp, nrows, gy0, H, xt, inside, km2);
+  }
+  // the tile's integer minima of the two differences
+  {
+    const uint32_t m0 = __reduce_min_sync(0xffffffffu, dmin2 & 0xffffu), m1 = __reduce_min_sync(0xffffffffu, dmin2 >> 16);
+    if (lane == 0) s_wmin[warp] = m0 | (m1 << 16);
+  }
+  __syncthreads();   // also: every read of HX0 / HX1 / HN0 is done, the candidate lists below borrow HX0
+  double* cand_d = reinterpret_cast<double*>(HX0);          // [2][256]
+  unsigned* cand_i = reinterpret_cast<unsigned*>(cand_d + 512);  // [2][256]
+  uint32_t cm2 = s_wmin[0];
 #pragma unroll
-    for (int i = 0; i < WF_VR; i++) {
-      const int gy = y0 + ry0 + i;
-      if (gy >= H) break;
-      const size_t ppix = (size_t)gy * Wp + gx;
-      if (gx >= W) { kqf[ppix] = 0u; mgf[ppix] = 0; continue; }
-      const bool touches = xt || (gy < WF_R) || (gy + WF_R >= H);
-      const uint32_t c0 = P0[(ry0 + i + WF_R) * WF_PP + x + WF_R], c1 = P1[(ry0 + i + WF_R) * WF_PP + x + WF_R];
-      const uint32_t mb = touches ? 0u : (mn0[i] & 0xffffu) - (uint32_t)kmin;
-      const uint32_t mg = touches ? 0u : (mn0[i] >> 16) - (uint32_t)kmin;
-      kqf[ppix] = ((c0 & 0xffffu) - kmin) | (((c0 >> 16) - kmin) << 8) | ((c1 - kmin) << 16) | (mb << 24);
-      mgf[ppix] = (uint8_t)mg;
-      // D (BGDehaze.py:20-21): max_R - max_B, max_R - max_G on the normalised image
-      const int mr = (int)mx1[i], mB = (int)(mx0[i] & 0xffffu), mG = (int)(mx0[i] >> 16);
-      const unsigned idx = (unsigned)((size_t)gy * W + gx);
-      const int d0i = mr - mB, d1i = mr - mG;
-      const int pr0 = (mr << 8) | mB, pr1 = (mr << 8) | mG;
-      if (d0i <= b0.di && pr0 != bp0) {
-        double d = s_nrm[mr - kmin] - s_nrm[mB - kmin];
-        if (d0i < b0.di || d < b0.d) { b0.di = d0i; b0.d = d; b0.idx = idx; bp0 = pr0; }  // rows go down: idx only grows
-      }
-      if (d1i <= b1.di && pr1 != bp1) {
-        double d = s_nrm[mr - kmin] - s_nrm[mG - kmin];
-        if (d1i < b1.di || d < b1.d) { b1.di = d1i; b1.d = d; b1.idx = idx; bp1 = pr1; }
-      }
+  for (int k = 1; k < 8; k++) cm2 = __vminu2(cm2, s_wmin[k]);
+  if (inside && nrows > 0) {
+    const unsigned idx0 = (unsigned)gy0 * (unsigned)W + (unsigned)gx;
+    if ((dmin2 & 0xffffu) == (cm2 & 0xffffu)) {
+      double bd = __longlong_as_double(0x7ff0000000000000ll); unsigned bi = 0xffffffffu;
+      wf_exact<0>(mx0, mx1, nrows, cm2 & 0xffffu, kmin, s_nrm, idx0, (unsigned)W, bd, bi);
+      const int slot = atomicAdd(&s_cnt[0], 1);
+      cand_d[slot] = bd; cand_i[slot] = bi;
     }
-  }
-  // block reduction, lexicographic: first index of the minimum
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    int oi0 = __shfl_xor_sync(0xffffffffu, b0.di, d), oi1 = __shfl_xor_sync(0xffffffffu, b1.di, d);
-    double o0 = __shfl_xor_sync(0xffffffffu, b0.d, d), o1 = __shfl_xor_sync(0xffffffffu, b1.d, d);
-    unsigned j0 = __shfl_xor_sync(0xffffffffu, b0.idx, d), j1 = __shfl_xor_sync(0xffffffffu, b1.idx, d);
-    if (cand_less(oi0, o0, j0, b0.di, b0.d, b0.idx)) { b0.di = oi0; b0.d = o0; b0.idx = j0; }
-    if (cand_less(oi1, o1, j1, b1.di, b1.d, b1.idx)) { b1.di = oi1; b1.d = o1; b1.idx = j1; }
-  }
-  __shared__ int s_di[8][2];
-  if ((tid & 31) == 0) {
-    ArgPartial a; a.d0 = b0.d; a.d1 = b1.d; a.i0 = b0.idx; a.i1 = b1.idx;
-    s_part[tid >> 5] = a; s_di[tid >> 5][0] = b0.di; s_di[tid >> 5][1] = b1.di;
+    if ((dmin2 >> 16) == (cm2 >> 16)) {
+      double bd = __longlong_as_double(0x7ff0000000000000ll); unsigned bi = 0xffffffffu;
+      wf_exact<1>(mx0, mx1, nrows, cm2 >> 16, kmin, s_nrm, idx0, (unsigned)W, bd, bi);
+      const int slot = atomicAdd(&s_cnt[1], 1);
+      cand_d[256 + slot] = bd; cand_i[256 + slot] = bi;
+    }
   }
   __syncthreads();
-  if (tid == 0) {
-    ArgPartial a = s_part[0];
-    int i0 = s_di[0][0], i1 = s_di[0][1];
-    for (int k = 1; k < 8; k++) {
-      ArgPartial b = s_part[k];
-      if (cand_less(s_di[k][0], b.d0, b.i0, i0, a.d0, a.i0)) { i0 = s_di[k][0]; a.d0 = b.d0; a.i0 = b.i0; }
-      if (cand_less(s_di[k][1], b.d1, b.i1, i1, a.d1, a.i1)) { i1 = s_di[k][1]; a.d1 = b.d1; a.i1 = b.i1; }
+  // warp 0 finishes difference 0, warp 1 difference 1: lexicographic (value, index) minimum of the candidates.
+  // A NaN D (range 0) never enters: the "nothing found" marker (inf, 0xffffffff) is left for bglight_finish_kernel
+  if (warp < 2) {
+    const int n = s_cnt[warp];
+    double bd = __longlong_as_double(0x7ff0000000000000ll); unsigned bi = 0xffffffffu;
+    for (int k = lane; k < n; k += 32) {
+      const double d = cand_d[warp * 256 + k]; const unsigned i = cand_i[warp * 256 + k];
+      if (lex_less(d, i, bd, bi)) { bd = d; bi = i; }
     }
-    // empty tile part or NaN D (range 0): leave the "nothing found" marker for bglight_finish_kernel
-    if (!(a.d0 == a.d0)) a.i0 = 0xffffffffu;
-    if (!(a.d1 == a.d1)) a.i1 = 0xffffffffu;
-    if (a.i0 == 0xffffffffu) a.d0 = __longlong_as_double(0x7ff0000000000000ll);
-    if (a.i1 == 0xffffffffu) a.d1 = __longlong_as_double(0x7ff0000000000000ll);
-    partials[(size_t)f * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x] = a;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, d); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, d);
+      if (lex_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+      ArgPartial* a = partials + ((size_t)f * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x);
+      if (bi == 0xffffffffu) bd = __longlong_as_double(0x7ff0000000000000ll);
+      if (warp == 0) { a->d0 = bd; a->i0 = bi; } else { a->d1 = bd; a->i1 = bi; }
+    }
   }
 }
 
