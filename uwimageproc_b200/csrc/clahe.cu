@@ -199,16 +199,21 @@ __device__ __forceinline__ int clahe_blend(float l11, float l12, float l21, floa
 constexpr int AP_THREADS = 256;
 
 // Processes `rows_per` image rows per block.  MODE 0: plane in / plane out.  MODE 1: bgr8 frame:
-// [optional stretch LUT on V + HSV->BGR->HSV round trip] -> CLAHE on V -> HSV->BGR, and optional
+// [PRE: stretch LUT on V + HSV->BGR->HSV round trip] -> CLAHE on V -> HSV->BGR, and optional
 // joint min/max of the output bytes into FrameState (dehaze D0, bgdehaze/main.py:17).
-template <int MODE>
+// A thread owns groups of four columns: the x interpolation of the four is formed once and reused down the band's rows,
+// and the loop body is four pixels long (the former sixteen-pixel body was 60 KB of code: a third of the warp stalls
+// were instruction fetches).
+constexpr int AP_ROWS = 8;   // rows whose y interpolation is tabulated per block
+template <int MODE, bool PRE>
 __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                  TileGeom g, int rows_per, const uint8_t* __restrict__ lut,
-                                                                 const uint8_t* __restrict__ prelut /*[n][256] or null*/,
+                                                                 const uint8_t* __restrict__ prelut /*[n][256], PRE only*/,
                                                                  int body_w, FrameState* fs) {
   extern __shared__ uint8_t s_lut[];  // [3][tx][256] when it fits
   __shared__ uint8_t s_pre[256];
   __shared__ int s_sdiv[256], s_hdiv[256];
+  __shared__ Interp s_iy[AP_ROWS];
   int f = blockIdx.y;
   int y0 = blockIdx.x * rows_per, y1 = min(y0 + rows_per, g.H);
   float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
@@ -223,10 +228,11 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
     for (int i = threadIdx.x; i < nbytes / 4; i += AP_THREADS) reinterpret_cast<uint32_t*>(s_lut)[i] = __ldg(s4 + i);
   }
   if (MODE == 1) {
-    s_pre[threadIdx.x] = prelut ? prelut[(size_t)f * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
+    s_pre[threadIdx.x] = PRE ? prelut[(size_t)f * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
     s_sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
     s_hdiv[threadIdx.x] = hsv_hdiv(threadIdx.x);
   }
+  if (threadIdx.x < AP_ROWS && y0 + (int)threadIdx.x < y1) s_iy[threadIdx.x] = interp_coord(y0 + threadIdx.x, inv_th, g.ty);
   __syncthreads();
   const uint8_t* L = staged ? s_lut : flut;
   int ty_off = staged ? ty_lo : 0;
@@ -234,7 +240,6 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
   const uint8_t* in = src + (size_t)f * n_px * (MODE ? 3 : 1);
   uint8_t* out = dst + (size_t)f * n_px * (MODE ? 3 : 1);
   unsigned int mn = 255, mx = 0;
-  const bool has_pre = (prelut != nullptr);
 
   auto lookup = [&](int v, const Interp& ix, const Interp& iy) {
     const uint8_t* r1 = L + (size_t)(iy.t1 - ty_off) * g.tx * 256;
@@ -243,59 +248,57 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
     float l21 = (float)r2[ix.t1 * 256 + v], l22 = (float)r2[ix.t2 * 256 + v];
     return clahe_blend(l11, l12, l21, l22, ix, iy);
   };
-  auto do_pixel = [&](int& b, int& gg, int& r, int x, const Interp& iy) {
-    bool tr = x < body_w;
+  auto do_pixel = [&](int& b, int& gg, int& r, bool tr, const Interp& ix, const Interp& iy) {
     int h, s, v;
-    if (has_pre) {  // histretch on V (intended order) fused in front, incl. its colour round trip
+    if (PRE) {  // histretch on V (intended order) fused in front, incl. its colour round trip
       bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
       hsv2bgr_u8(h, s, s_pre[v], tr, b, gg, r);
     }
     bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
-    Interp ix = interp_coord(x, inv_tw, g.tx);
     v = lookup(v, ix, iy);
     hsv2bgr_u8(h, s, v, tr, b, gg, r);
     mn = min(mn, (unsigned)imin3(b, gg, r));
     mx = max(mx, (unsigned)imax3(b, gg, r));
   };
 
-  bool vec = (g.W % 16 == 0) && (((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0);
+  const bool vec = (g.W % 4 == 0) && (((((uintptr_t)in) | ((uintptr_t)out)) & 3) == 0) && (body_w % 4 == 0);
   if (vec) {
-    int gpr = g.W / 16;
-    int total = (y1 - y0) * gpr;
-    for (int i = threadIdx.x; i < total; i += AP_THREADS) {
-      int ry = i / gpr, gx = i - ry * gpr;
-      int y = y0 + ry, x = gx * 16;
-      Interp iy = interp_coord(y, inv_th, g.ty);
-      if (MODE == 0) {
-        uint4 a = __ldg(reinterpret_cast<const uint4*>(in + (size_t)y * g.W + x));
-        uint32_t w[4] = {a.x, a.y, a.z, a.w};
+    const int gpr = g.W / 4, wpr = MODE ? 3 * gpr : gpr;   // column groups, words per row
+    for (int gx = threadIdx.x; gx < gpr; gx += AP_THREADS) {
+      const int x = 4 * gx;
+      const bool tr = x < body_w;
+      Interp ix[4];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          int v = (w[k >> 2] >> ((k & 3) * 8)) & 0xff;
-          Interp ix = interp_coord(x + k, inv_tw, g.tx);
-          int o = lookup(v, ix, iy);
-          w[k >> 2] = (w[k >> 2] & ~(0xffu << ((k & 3) * 8))) | ((uint32_t)o << ((k & 3) * 8));
+      for (int k = 0; k < 4; k++) ix[k] = interp_coord(x + k, inv_tw, g.tx);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(in) + (size_t)y0 * wpr + (MODE ? 3 * gx : gx);
+      uint32_t* o = reinterpret_cast<uint32_t*>(out) + (size_t)y0 * wpr + (MODE ? 3 * gx : gx);
+      uint32_t n0 = __ldg(q), n1 = MODE ? __ldg(q + 1) : 0u, n2 = MODE ? __ldg(q + 2) : 0u;
+#pragma unroll 1
+      for (int y = y0; y < y1; y++) {
+        const uint32_t w0 = n0, w1 = n1, w2 = n2;
+        if (y + 1 < y1) {   // the next row's words are on their way while this row is worked on
+          q += wpr;
+          n0 = __ldg(q);
+          if (MODE) { n1 = __ldg(q + 1); n2 = __ldg(q + 2); }
         }
-        *reinterpret_cast<uint4*>(out + (size_t)y * g.W + x) = make_uint4(w[0], w[1], w[2], w[3]);
-      } else {
-        const uint4* q = reinterpret_cast<const uint4*>(in + ((size_t)y * g.W + x) * 3);
-        uint4 a = __ldg(q), bq = __ldg(q + 1), c = __ldg(q + 2);
-        uint32_t w[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          int i0 = 3 * k, i1 = 3 * k + 1, i2 = 3 * k + 2;
-          int b = (w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xff;
-          int gg = (w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xff;
-          int r = (w[i2 >> 2] >> ((i2 & 3) * 8)) & 0xff;
-          do_pixel(b, gg, r, x + k, iy);
-          w[i0 >> 2] = (w[i0 >> 2] & ~(0xffu << ((i0 & 3) * 8))) | ((uint32_t)b << ((i0 & 3) * 8));
-          w[i1 >> 2] = (w[i1 >> 2] & ~(0xffu << ((i1 & 3) * 8))) | ((uint32_t)gg << ((i1 & 3) * 8));
-          w[i2 >> 2] = (w[i2 >> 2] & ~(0xffu << ((i2 & 3) * 8))) | ((uint32_t)r << ((i2 & 3) * 8));
+        const Interp iy = (y - y0 < AP_ROWS) ? s_iy[y - y0] : interp_coord(y, inv_th, g.ty);
+        if (MODE == 0) {
+          const int v0 = lookup(w0 & 0xff, ix[0], iy), v1 = lookup((w0 >> 8) & 0xff, ix[1], iy);
+          const int v2 = lookup((w0 >> 16) & 0xff, ix[2], iy), v3 = lookup(w0 >> 24, ix[3], iy);
+          o[0] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+        } else {
+          int b0 = w0 & 0xff, g0 = (w0 >> 8) & 0xff, r0 = (w0 >> 16) & 0xff, b1 = w0 >> 24;
+          int g1 = w1 & 0xff, r1 = (w1 >> 8) & 0xff, b2 = (w1 >> 16) & 0xff, g2 = w1 >> 24;
+          int r2 = w2 & 0xff, b3 = (w2 >> 8) & 0xff, g3 = (w2 >> 16) & 0xff, r3 = w2 >> 24;
+          do_pixel(b0, g0, r0, tr, ix[0], iy);
+          do_pixel(b1, g1, r1, tr, ix[1], iy);
+          do_pixel(b2, g2, r2, tr, ix[2], iy);
+          do_pixel(b3, g3, r3, tr, ix[3], iy);
+          o[0] = (uint32_t)b0 | ((uint32_t)g0 << 8) | ((uint32_t)r0 << 16) | ((uint32_t)b1 << 24);
+          o[1] = (uint32_t)g1 | ((uint32_t)r1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)g2 << 24);
+          o[2] = (uint32_t)r2 | ((uint32_t)b3 << 8) | ((uint32_t)g3 << 16) | ((uint32_t)r3 << 24);
         }
-        uint4* o = reinterpret_cast<uint4*>(out + ((size_t)y * g.W + x) * 3);
-        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        o += wpr;
       }
     }
   } else {
@@ -304,13 +307,13 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
       int ry = i / g.W, x = i - ry * g.W;
       int y = y0 + ry;
       Interp iy = interp_coord(y, inv_th, g.ty);
+      Interp ix = interp_coord(x, inv_tw, g.tx);
       if (MODE == 0) {
-        Interp ix = interp_coord(x, inv_tw, g.tx);
         out[(size_t)y * g.W + x] = (uint8_t)lookup(in[(size_t)y * g.W + x], ix, iy);
       } else {
         const uint8_t* p = in + ((size_t)y * g.W + x) * 3;
         int b = p[0], gg = p[1], r = p[2];
-        do_pixel(b, gg, r, x, iy);
+        do_pixel(b, gg, r, x < body_w, ix, iy);
         uint8_t* o = out + ((size_t)y * g.W + x) * 3;
         o[0] = (uint8_t)b; o[1] = (uint8_t)gg; o[2] = (uint8_t)r;
       }
@@ -390,10 +393,12 @@ static int clahe_common(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
   while (rows_per > 1 && (long long)cdiv(h, rows_per) * n < (long long)ctx->sm_count * 4) rows_per /= 2;
   dim3 grid3(cdiv(h, rows_per), n);
   size_t smem = (size_t)3 * (tx <= 32 ? tx : 0) * 256;
-  if (frame)
-    UWIP_LAUNCH(ctx, "clahe_apply", clahe_apply_kernel<1>, grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl, d_prelut, bw, fs);
+  if (frame && d_prelut)
+    UWIP_LAUNCH(ctx, "clahe_apply", (clahe_apply_kernel<1, true>), grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl, d_prelut, bw, fs);
+  else if (frame)
+    UWIP_LAUNCH(ctx, "clahe_apply", (clahe_apply_kernel<1, false>), grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl, d_prelut, bw, fs);
   else
-    UWIP_LAUNCH(ctx, "clahe_apply", clahe_apply_kernel<0>, grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl,
+    UWIP_LAUNCH(ctx, "clahe_apply", (clahe_apply_kernel<0, false>), grid3, AP_THREADS, smem, d_src, d_dst, g, rows_per, d_tl,
                 (const uint8_t*)nullptr, bw, (FrameState*)nullptr);
   return UWIP_OK;
 }
