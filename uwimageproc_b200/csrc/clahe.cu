@@ -193,7 +193,66 @@ __device__ __forceinline__ int clahe_blend(float l11, float l12, float l21, floa
   float top = __fadd_rn(__fmul_rn(l11, ix.a1), __fmul_rn(l12, ix.a));
   float bot = __fadd_rn(__fmul_rn(l21, ix.a1), __fmul_rn(l22, ix.a));
   float res = __fadd_rn(__fmul_rn(top, iy.a1), __fmul_rn(bot, iy.a));
-  return sat_rint_u8(res);
+  return __float_as_int(__fadd_rn(res, 8388608.0f)) & 0xff;   // rint of a blend of four bytes: in [0, 255], see ap_to_byte
+}
+
+// ---- colour arithmetic of the apply kernel: the same values as hsv2bgr_u8 / bgr2hsv_u8 (common.cuh), fewer instructions ----
+// Float -> byte: the products below lie in [0, 256), so adding 2^23 leaves rint(x) (round to nearest even, as cvt.rni) or
+// floor(x) (add rounding toward zero, as cvt.rzi on a non-negative value) in the low mantissa bits: one FADD instead of a
+// conversion and two clamps.  The results keep the bit pattern of 2^23 as a common bias (AP_BIAS + k): maxima, minima and
+// differences do not care, the byte is picked by PRMT when the words are packed.
+constexpr int AP_BIAS = 0x4B000000;
+__device__ __forceinline__ int ap_to_byte(float x, bool trunc_mode) {
+  return __float_as_int(trunc_mode ? __fadd_rz(x, 8388608.0f) : __fadd_rn(x, 8388608.0f));
+}
+// sector table of cvtColor(HSV2BGR) as weights: channel = v * (1 - s * w), w = A + B * f with (A, B) = (0,0) for tab[0] = v,
+// (1,0) for tab[1] = v(1-s), (0,1) for tab[2] = v(1-s f), (1,-1) for tab[3] = v(1-s(1-f)).  fma(B, f, A) and fma(-s, w, 1) round
+// exactly like the subtractions of the scalar code (each is one rounding of the same real number), and the six-way
+// branch on the sector disappears.  Row = sector, columns A_b B_b A_g B_g A_r B_r - -.
+__device__ __forceinline__ void ap_fill_sector_table(float* tab /*[6][8]*/, int t) {
+  if (t < 48) {
+    const int sec = t >> 3, col = t & 7;
+    // (b, g, r) <- tab index: {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+    // two bits per channel (b g r), six bits per sector
+    const unsigned long long codes = 0x1cull | (0x12ull << 6) | (0x31ull << 12) | (0x09ull << 18) | (0x07ull << 24) | (0x24ull << 30);
+    float val = 0.0f;
+    if (col < 6) {
+      const int k = (int)(codes >> (6 * sec + 2 * (2 - (col >> 1)))) & 3;
+      const float A = (k == 1 || k == 3) ? 1.0f : 0.0f, B = (k == 2) ? 1.0f : (k == 3 ? -1.0f : 0.0f);
+      val = (col & 1) ? B : A;
+    }
+    tab[t] = val;
+  }
+}
+// H in [0, 180) (always true for the output of bgr2hsv), S, V bytes -> b, g, r carrying AP_BIAS
+__device__ __forceinline__ void ap_hsv2bgr(int H, int S, int V, bool trunc_mode, const float* __restrict__ tab, int& b, int& g, int& r) {
+  const float h = __fmul_rn((float)H, 6.0f / 180.0f);
+  const float s = __fmul_rn((float)S, 1.0f / 255.0f);
+  const float v = __fmul_rn((float)V, 1.0f / 255.0f);
+  const float hz = __fadd_rz(h, 8388608.0f);            // 2^23 + floor(h)
+  const float f = __fsub_rn(h, __fsub_rn(hz, 8388608.0f));
+  const int sec = __float_as_int(hz) & 7;               // 0 .. 5
+  const float4 w4 = *reinterpret_cast<const float4*>(tab + 8 * sec);
+  const float2 w2 = *reinterpret_cast<const float2*>(tab + 8 * sec + 4);
+  const float fb = __fmul_rn(v, __fmaf_rn(-s, __fmaf_rn(w4.y, f, w4.x), 1.0f));
+  const float fg = __fmul_rn(v, __fmaf_rn(-s, __fmaf_rn(w4.w, f, w4.z), 1.0f));
+  const float fr = __fmul_rn(v, __fmaf_rn(-s, __fmaf_rn(w2.y, f, w2.x), 1.0f));
+  b = ap_to_byte(__fmul_rn(fb, 255.0f), trunc_mode);
+  g = ap_to_byte(__fmul_rn(fg, 255.0f), trunc_mode);
+  r = ap_to_byte(__fmul_rn(fr, 255.0f), trunc_mode);
+}
+// bgr2hsv_u8 on values that share an additive bias (0 or AP_BIAS); h, s, v come out plain
+__device__ __forceinline__ void ap_bgr2hsv(int b, int g, int r, const int* __restrict__ sdiv, const int* __restrict__ hdiv, int& h, int& s, int& v) {
+  const int vm = imax3(b, g, r);
+  const int d = vm - imin3(b, g, r);
+  v = vm & 0xff;
+  s = (d * sdiv[v] + (1 << 11)) >> 12;
+  const int h0 = (vm == r) ? (g - b) : ((vm == g) ? (b - r + 2 * d) : (r - g + 4 * d));
+  h = (h0 * hdiv[d] + (1 << 11)) >> 12;
+  if (h < 0) h += 180;
+}
+__device__ __forceinline__ uint32_t ap_pack4(int a, int b, int c, int d) {   // low bytes of four values
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
 constexpr int AP_THREADS = 256;
@@ -214,6 +273,7 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
   __shared__ uint8_t s_pre[256];
   __shared__ int s_sdiv[256], s_hdiv[256];
   __shared__ Interp s_iy[AP_ROWS];
+  __shared__ __align__(16) float s_sec[48];
   int f = blockIdx.y;
   int y0 = blockIdx.x * rows_per, y1 = min(y0 + rows_per, g.H);
   float inv_tw = __fdiv_rn(1.0f, (float)g.tw), inv_th = __fdiv_rn(1.0f, (float)g.th);
@@ -231,6 +291,7 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
     s_pre[threadIdx.x] = PRE ? prelut[(size_t)f * 256 + threadIdx.x] : (uint8_t)threadIdx.x;
     s_sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
     s_hdiv[threadIdx.x] = hsv_hdiv(threadIdx.x);
+    ap_fill_sector_table(s_sec, threadIdx.x);
   }
   if (threadIdx.x < AP_ROWS && y0 + (int)threadIdx.x < y1) s_iy[threadIdx.x] = interp_coord(y0 + threadIdx.x, inv_th, g.ty);
   __syncthreads();
@@ -239,7 +300,7 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
   size_t n_px = (size_t)g.W * g.H;
   const uint8_t* in = src + (size_t)f * n_px * (MODE ? 3 : 1);
   uint8_t* out = dst + (size_t)f * n_px * (MODE ? 3 : 1);
-  unsigned int mn = 255, mx = 0;
+  int mn = AP_BIAS + 255, mx = AP_BIAS;   // of the biased output bytes
 
   auto lookup = [&](int v, const Interp& ix, const Interp& iy) {
     const uint8_t* r1 = L + (size_t)(iy.t1 - ty_off) * g.tx * 256;
@@ -251,14 +312,14 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
   auto do_pixel = [&](int& b, int& gg, int& r, bool tr, const Interp& ix, const Interp& iy) {
     int h, s, v;
     if (PRE) {  // histretch on V (intended order) fused in front, incl. its colour round trip
-      bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
-      hsv2bgr_u8(h, s, s_pre[v], tr, b, gg, r);
+      ap_bgr2hsv(b, gg, r, s_sdiv, s_hdiv, h, s, v);
+      ap_hsv2bgr(h, s, s_pre[v], tr, s_sec, b, gg, r);
     }
-    bgr2hsv_u8(b, gg, r, s_sdiv, s_hdiv, h, s, v);
+    ap_bgr2hsv(b, gg, r, s_sdiv, s_hdiv, h, s, v);
     v = lookup(v, ix, iy);
-    hsv2bgr_u8(h, s, v, tr, b, gg, r);
-    mn = min(mn, (unsigned)imin3(b, gg, r));
-    mx = max(mx, (unsigned)imax3(b, gg, r));
+    ap_hsv2bgr(h, s, v, tr, s_sec, b, gg, r);   // b, gg, r carry AP_BIAS from here on
+    mn = min(mn, imin3(b, gg, r));
+    mx = max(mx, imax3(b, gg, r));
   };
 
   const bool vec = (g.W % 4 == 0) && (((((uintptr_t)in) | ((uintptr_t)out)) & 3) == 0) && (body_w % 4 == 0);
@@ -294,9 +355,9 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
           do_pixel(b1, g1, r1, tr, ix[1], iy);
           do_pixel(b2, g2, r2, tr, ix[2], iy);
           do_pixel(b3, g3, r3, tr, ix[3], iy);
-          o[0] = (uint32_t)b0 | ((uint32_t)g0 << 8) | ((uint32_t)r0 << 16) | ((uint32_t)b1 << 24);
-          o[1] = (uint32_t)g1 | ((uint32_t)r1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)g2 << 24);
-          o[2] = (uint32_t)r2 | ((uint32_t)b3 << 8) | ((uint32_t)g3 << 16) | ((uint32_t)r3 << 24);
+          o[0] = ap_pack4(b0, g0, r0, b1);
+          o[1] = ap_pack4(g1, r1, b2, g2);
+          o[2] = ap_pack4(r2, b3, g3, r3);
         }
         o += wpr;
       }
@@ -320,11 +381,10 @@ __global__ void __launch_bounds__(AP_THREADS) clahe_apply_kernel(const uint8_t* 
     }
   }
   if (MODE == 1 && fs) {
-    mn = warp_reduce_min_u32(mn);
-    mx = warp_reduce_max_u32(mx);
+    const unsigned umn = warp_reduce_min_u32((unsigned)(mn & 0xff)), umx = warp_reduce_max_u32((unsigned)(mx & 0xff));
     if ((threadIdx.x & 31) == 0) {
-      atomicMin(&fs[f].kmin, mn);
-      atomicMax(&fs[f].kmax, mx);
+      atomicMin(&fs[f].kmin, umn);
+      atomicMax(&fs[f].kmax, umx);
     }
   }
 }
