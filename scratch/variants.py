@@ -6,8 +6,9 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "one": [],
-    "one_a160": ["-DGP_GF1A_ACC_REGS=160", "-DGP_GF2A_ACC_REGS=136"],
+    "wide": [],
+    "narrow": ["-DGP_NARROW=1"],
+    "narrow_b112": ["-DGP_NARROW=1", "-DGP_B_ACC_REGS=112", "-DGP_GF2A_ACC_REGS=152"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 
@@ -21,14 +22,14 @@ def build():
         assert r.returncode == 0, r.stderr[-3000:]
         sp = [l for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
         lib = os.path.join(OUT, "libuwip_%s.so" % name)
-        r = subprocess.run([B._nvcc(), "-shared", "-o", lib] + objs + [obj, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
+        r = subprocess.run([B._nvcc(), "-shared", "-o", lib] + objs + [obj, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lnvjpeg_static", "-lculibos", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         print(name, flags, "spills:", len(sp))
 
 def run():
     for name in VARIANTS:
         env = dict(os.environ, UWIP_LIB=os.path.join(OUT, "libuwip_%s.so" % name))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--frames", "86", "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--frames", "144", "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline"],
                            capture_output=True, text=True, env=env)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])

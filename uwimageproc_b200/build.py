@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libuwip.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["cabi.cu", "histretch.cu", "clahe.cu", "dehaze.cu", "synth.cu", "blurmetric.cu", "jpegio.cu"]
+SOURCES = ["cabi.cu", "histretch.cu", "clahe.cu", "dehaze.cu", "dehaze_gf1a.cu", "synth.cu", "blurmetric.cu", "jpegio.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -58,22 +58,28 @@
 #ifndef GP_TRACE
 #define GP_TRACE 0              // timing experiment: clock stamps of the three roles for 64 rows of CTA (0,0,0)
 #endif
+#ifndef GP_NARROW
+#define GP_NARROW 0             // 1: strips of 128 quads - four ACC warps in one warpgroup, four auxiliary warps in another with their own (small) register count
+#endif
+#ifndef GP_AUX_REGS
+#define GP_AUX_REGS 88          // GP_NARROW: registers of an auxiliary thread
+#endif
 #ifndef GP_GF1A_ACC_REGS
-#define GP_GF1A_ACC_REGS (GP_NGRP_SEL == 1 ? 152 : 96)
+#define GP_GF1A_ACC_REGS (GP_NARROW ? 176 : GP_NGRP_SEL == 1 ? 152 : 96)
 #endif
 #ifndef GP_GF2A_ACC_REGS
-#define GP_GF2A_ACC_REGS (GP_NGRP_SEL == 1 ? 128 : 96)
+#define GP_GF2A_ACC_REGS (GP_NARROW ? 168 : GP_NGRP_SEL == 1 ? 128 : 96)
 #endif
 #ifndef GP_B_ACC_REGS
-#define GP_B_ACC_REGS (GP_NGRP_SEL == 1 ? 136 : 80)
+#define GP_B_ACC_REGS (GP_NARROW ? 128 : GP_NGRP_SEL == 1 ? 136 : 80)
 #endif
 
 #ifndef GP_NGRP_SEL
 #define GP_NGRP_SEL 1                 // 2: two ACC threads per quad, each with half of the running sums (measured slower: r2_summary.md)
 #endif
-constexpr int GP_NT = 160;            // quads of a strip (quad 0 is the zero guard) = ACC worker threads per moment group
+constexpr int GP_NT = GP_NARROW ? 128 : 160;   // quads of a strip (quad 0 is the zero guard) = ACC worker threads per moment group
 constexpr int GP_NGRP = GP_NGRP_SEL;  // ACC moment groups
-constexpr int GP_NAUX = GP_NGRP == 1 ? 3 : 2;   // auxiliary warps
+constexpr int GP_NAUX = GP_NARROW ? 4 : GP_NGRP == 1 ? 3 : 2;   // auxiliary warps
 constexpr int GP_SOLVE_THREADS = 256; // two warpgroups (threads 0..255)
 constexpr int GP_ACC_THREADS = GP_NGRP * GP_NT + 32 * GP_NAUX;   // 256 (two warpgroups) or 384 (three)
 constexpr int GP_THREADS = GP_ACC_THREADS + GP_SOLVE_THREADS;
@@ -87,7 +93,8 @@ static_assert(GP_GP >= GP_NT && GP_NGRP * GP_NT + 32 * GP_NAUX == GP_ACC_THREADS
 constexpr double GP_PSCALE = 268435456.0, GP_PINV = 1.0 / 268435456.0;
 constexpr double GP_T_PMAX = 1.0, GP_S_PMAX = 1.6;
 // registers left for a SOLVE thread when an ACC / AUX thread takes `acc` (pool = threads x launch registers), in units of 8
-#define GP_SOLVE_REGS_FOR(acc) (GP_NGRP_SEL == 1 ? 256 - (acc) : ((((96 * 640 - 384 * (acc)) / 256) / 8) * 8))
+#define GP_SOLVE_REGS_FOR(acc) \
+  (GP_NARROW ? ((((65536 - 128 * (acc) - 128 * GP_AUX_REGS) / 256) / 8) * 8) : GP_NGRP_SEL == 1 ? 256 - (acc) : ((((96 * 640 - 384 * (acc)) / 256) / 8) * 8))
 
 // wait for the phase with the given parity; the suspend-time hint lets the hardware park the warp until the phase
 // completes (or the time runs out) instead of re-issuing the test every few cycles
@@ -598,8 +605,10 @@ __device__ __forceinline__ void gp_set_regs() {
 template <class P>
 __global__ void __launch_bounds__(GP_THREADS, 1) gp_kernel(GfCommon gc, GfGeom gg) {
   typedef GpSmem<P> L;
-  static_assert(GP_ACC_THREADS * P::ACC_REGS + GP_SOLVE_THREADS * P::SOLVE_REGS <= GP_THREADS * GP_LAUNCH_REGS && P::SOLVE_REGS <= 255 &&
-                P::NSTAGE >= 2 && P::NSTAGE <= 4, "register pool / ring");
+  static_assert((GP_NARROW ? GP_NT * P::ACC_REGS + 32 * GP_NAUX * GP_AUX_REGS : GP_ACC_THREADS * P::ACC_REGS) + GP_SOLVE_THREADS * P::SOLVE_REGS <=
+                        GP_THREADS * GP_LAUNCH_REGS && P::SOLVE_REGS <= 255 && P::ACC_REGS <= 255 && P::NSTAGE >= 2 && P::NSTAGE <= 4,
+                "register pool / ring");
+  static_assert(!GP_NARROW || (GP_NGRP == 1 && GP_NT == 128 && GP_NAUX == 4), "narrow layout: one warpgroup of ACC workers, one of auxiliary warps");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
   const int t = threadIdx.x;
@@ -629,6 +638,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gp_kernel(GfCommon gc, GfGeom g
   if (t < GP_SOLVE_THREADS) {
     gp_set_regs<P::SOLVE_REGS>();
     gp_solve<P>(gc, gg, smem_raw);
+  } else if constexpr (GP_NARROW) {
+    if (t < GP_SOLVE_THREADS + GP_NT) {
+      gp_set_regs<P::ACC_REGS>();
+      gp_acc_worker<P, 2>(gc, gg, smem_raw);
+    } else {
+      gp_set_regs<GP_AUX_REGS>();
+      gp_aux<P>(gc, gg, smem_raw);
+    }
   } else {
     gp_set_regs<P::ACC_REGS>();
     if constexpr (GP_NGRP == 1) {
