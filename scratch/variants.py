@@ -6,9 +6,10 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "wide": [],
+    "w_g2a144": ["-DGP_GF2A_ACC_REGS=144"],
     "narrow": ["-DGP_NARROW=1"],
-    "narrow_b112": ["-DGP_NARROW=1", "-DGP_B_ACC_REGS=112", "-DGP_GF2A_ACC_REGS=152"],
+    "narrow_g2a152": ["-DGP_NARROW=1", "-DGP_GF2A_ACC_REGS=152"],
+    "narrow_g2a136": ["-DGP_NARROW=1", "-DGP_GF2A_ACC_REGS=136"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 
@@ -20,11 +21,11 @@ def build():
         obj = os.path.join(OUT, "dehaze_%s.o" % name)
         r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, "dehaze.cu"), "-o", obj], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
-        sp = [l for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
+        sp = [l.strip() for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
         lib = os.path.join(OUT, "libuwip_%s.so" % name)
         r = subprocess.run([B._nvcc(), "-shared", "-o", lib] + objs + [obj, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lnvjpeg_static", "-lculibos", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
-        print(name, flags, "spills:", len(sp))
+        print(name, flags, "spills:", sp)
 
 def run():
     for name in VARIANTS:

@@ -309,12 +309,10 @@ static int gp_launch(uwip_ctx* ctx, const char* tag, int func_id, const GfCommon
   }
   gg.seg_h = cdiv(H, best);
   int segs = cdiv(H, gg.seg_h);
+  static_assert(GpSmem<P>::bytes <= 227 * 1024, "shared memory");
   size_t smem = GpSmem<P>::bytes;
   UWIP_CUDA(ctx, uwip_func_smem(ctx, func_id, gp_kernel<P>, smem));
   dim3 grid(strips, segs, n);
   UWIP_LAUNCH(ctx, tag, gp_kernel<P>, grid, GP_THREADS, smem, gc, gg);
   return UWIP_OK;
 }
-static_assert(GpSmem<PipGFq>::bytes <= 227 * 1024 && GpSmem<PipGF1a>::bytes <= 227 * 1024 && GpSmem<PipGF2a>::bytes <= 227 * 1024 && GpSmem<PipGF1b>::bytes <= 227 * 1024 &&
-              GpSmem<PipGF2b>::bytes <= 227 * 1024, "shared memory");
-

@@ -68,7 +68,7 @@
 #define GP_GF1A_ACC_REGS (GP_NARROW ? 176 : GP_NGRP_SEL == 1 ? 152 : 96)
 #endif
 #ifndef GP_GF2A_ACC_REGS
-#define GP_GF2A_ACC_REGS (GP_NARROW ? 168 : GP_NGRP_SEL == 1 ? 128 : 96)
+#define GP_GF2A_ACC_REGS (GP_NARROW ? 168 : GP_NGRP_SEL == 1 ? 144 : 96)
 #endif
 #ifndef GP_B_ACC_REGS
 #define GP_B_ACC_REGS (GP_NARROW ? 128 : GP_NGRP_SEL == 1 ? 136 : 80)
@@ -226,9 +226,8 @@ enum { GPB_FULL = 0, GPB_READY = 4, GPB_EMPTY = 8, GPB_TFULL = 12, GPB_TEMPTY = 
 template <class P>
 struct GpSmem {
   static constexpr int NT = GP_NT, GP = GP_GP, NI = P::NI, ND = P::ND, NSTAGE = P::NSTAGE;
-  // one published row: Pd01 [ND][NT] double2 | Pd2 [ND][NT] f64 | Gd [ND][GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GP] u32
-  static constexpr size_t off_d2 = (size_t)ND * NT * 16;
-  static constexpr size_t off_gd = off_d2 + (size_t)ND * NT * 8;
+  // one published row: Pd [ND][NT] 4 x f64 (inclusive in-quad prefixes) | Gd [ND][GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GP] u32
+  static constexpr size_t off_gd = (size_t)ND * NT * 32;
   static constexpr size_t off_pi = off_gd + (size_t)ND * GP * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t stage_bytes = (off_gi + (size_t)NI * GP * 4 + 127) & ~(size_t)127;
@@ -239,15 +238,14 @@ struct GpSmem {
 };
 
 struct GpStage {
-  double2* Pd01; double* Pd2; double* Gd; uint4* Pi; uint32_t* Gi;
+  double2* Pd; double* Gd; uint4* Pi; uint32_t* Gi;   // Pd: two double2 per quad and moment: (p0, p1), (p2, p3 = quad total)
 };
 template <class P>
 __device__ __forceinline__ GpStage gp_stage(unsigned char* smem, int s) {
   typedef GpSmem<P> L;
   unsigned char* b = smem + (size_t)s * L::stage_bytes;
   GpStage g;
-  g.Pd01 = reinterpret_cast<double2*>(b);
-  g.Pd2 = reinterpret_cast<double*>(b + L::off_d2);
+  g.Pd = reinterpret_cast<double2*>(b);
   g.Gd = reinterpret_cast<double*>(b + L::off_gd);
   g.Pi = reinterpret_cast<uint4*>(b + L::off_pi);
   g.Gi = reinterpret_cast<uint32_t*>(b + L::off_gi);
@@ -399,8 +397,8 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
         for (int k = (G == 1 ? P::NDA : 0); k < (G == 0 ? P::NDA : ND); k++) {
           const double p0 = Acc::to_double(Vl[0][k]), p1 = p0 + Acc::to_double(Vl[1][k]), p2 = p1 + Acc::to_double(Vl[2][k]),
                        p3 = p2 + Acc::to_double(Vl[3][k]);
-          st.Pd01[k * NT + t] = make_double2(p0, p1);
-          st.Pd2[k * NT + t] = p2;
+          st.Pd[(k * NT + t) * 2] = make_double2(p0, p1);
+          st.Pd[(k * NT + t) * 2 + 1] = make_double2(p2, p3);
           st.Gd[k * GP + t] = p3;
         }
       }
@@ -504,23 +502,24 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       si[0][k] = Wq - (h ? a0 : 0u) + b.x;
       si[1][k] = Wq - a1 + b.y;
     }
+    // pixel c of the quad: (G[thi-1] - G[tlo-1]) - p_tlo[c-1] + p_thi[c].  This thread has c = 2h, 2h+1: the pair of quad thi is
+    // one 16-byte load, p_tlo[2h] one 8-byte load, and p_tlo[2h-1] is p_tlo[1] for h = 1 and element 0 of quad 0 - the zero
+    // guard of every moment row - for h = 0: the same instructions for both halves, no branch between the moments, all
+    // addresses a per-thread base plus a constant (a branch per moment kept the loads of the moments from overlapping)
+    const double* Pd = reinterpret_cast<const double*>(st.Pd);
+    const double2* hi_p = st.Pd + thi * 2 + h;
+    const double* lo1_p = Pd + tlo * 4 + 2 * h;
+    const double* lo0_p = h ? Pd + tlo * 4 + 1 : Pd;
 #pragma unroll
     for (int k = 0; k < ND; k++) {
-      const double Gl = st.Gd[k * GP + tlo - 1];
-      const double Wq = st.Gd[k * GP + thi - 1] - Gl;
-      if (h == 0) {
-        const double2 b = st.Pd01[k * NT + thi];
-        const double a0 = st.Pd01[k * NT + tlo].x;
-        sd[0][k] = Wq + b.x; sd[1][k] = (Wq - a0) + b.y;
-      } else {
-        const double a1 = st.Pd01[k * NT + tlo].y, a2 = st.Pd2[k * NT + tlo], b2 = st.Pd2[k * NT + thi];
-        sd[0][k] = (Wq - a1) + b2;
-        sd[1][k] = (st.Gd[k * GP + thi] - Gl) - a2;  // the whole quad thi is inside: totals up to and including it
-      }
+      const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
+      const double2 b = hi_p[k * NT * 2];
+      sd[0][k] = (Wq - lo0_p[k * NT * 4]) + b.x;
+      sd[1][k] = (Wq - lo1_p[k * NT * 4]) + b.y;
     }
   } else {
     const uint32_t* Pis = reinterpret_cast<const uint32_t*>(st.Pi);
-    const double* P01 = reinterpret_cast<const double*>(st.Pd01);
+    const double* Pd = reinterpret_cast<const double*>(st.Pd);
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
       const int z = 4 * tq + 2 * h + cc;
@@ -533,10 +532,10 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       }
 #pragma unroll
       for (int k = 0; k < ND; k++) {
-        // prefix element (z&3)-1 of quad z>>2: elements 0,1 live in Pd01, 2 in Pd2
+        // prefix element (z&3)-1 of quad z>>2
         const int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-        double pl = (el < 0) ? 0.0 : (el < 2 ? P01[(k * NT + (zl >> 2)) * 2 + el] : st.Pd2[k * NT + (zl >> 2)]);
-        double ph = (eh < 0) ? 0.0 : (eh < 2 ? P01[(k * NT + (zh >> 2)) * 2 + eh] : st.Pd2[k * NT + (zh >> 2)]);
+        double pl = (el < 0) ? 0.0 : Pd[(k * NT + (zl >> 2)) * 4 + el];
+        double ph = (eh < 0) ? 0.0 : Pd[(k * NT + (zh >> 2)) * 4 + eh];
         sd[cc][k] = (st.Gd[k * GP + (zh >> 2) - 1] + ph) - (st.Gd[k * GP + (zl >> 2) - 1] + pl);
       }
     }
