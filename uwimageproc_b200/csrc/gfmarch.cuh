@@ -38,6 +38,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
   unsigned a = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void cp_async4(void* smem, const void* g) {
   unsigned a = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(g) : "memory");
@@ -282,7 +286,7 @@ static GfGeom gf_geometry(int W, int H, int r) {
   GfGeom g;
   g.W = W; g.H = H; g.Wp = (W + 3) & ~3; g.r = r;
   g.HL = (r + 3) & ~3;
-  int sw_max = std::min(4 * (GP_NT - 1) - 2 * g.HL, GP_MAXSW);   // quads per strip (ACC) and pixel pairs per strip (SOLVE)
+  int sw_max = std::min(4 * (GP_NTR - 1) - 2 * g.HL, GP_MAXSW);   // quads per strip (ACC) and pixel pairs per strip (SOLVE)
   int strips = cdiv(W, sw_max);
   g.SW = (cdiv(W, strips) + 3) & ~3;
   g.NQ = 1 + (2 * g.HL + g.SW) / 4;

@@ -78,6 +78,7 @@
 #define GP_NGRP_SEL 1                 // 2: two ACC threads per quad, each with half of the running sums (measured slower: r2_summary.md)
 #endif
 constexpr int GP_NT = GP_NARROW ? 128 : 160;   // quads of a strip (quad 0 is the zero guard) = ACC worker threads per moment group
+constexpr int GP_NTR = GP_NT < 152 ? GP_NT : 152;   // quads of a strip that can hold data (gf_geometry keeps NQ within it): the pitch of the TMA ring rows
 constexpr int GP_NGRP = GP_NGRP_SEL;  // ACC moment groups
 constexpr int GP_NAUX = GP_NARROW ? 4 : GP_NGRP == 1 ? 3 : 2;   // auxiliary warps
 constexpr int GP_SOLVE_THREADS = 256; // two warpgroups (threads 0..255)
@@ -234,7 +235,8 @@ struct GpSmem {
   static constexpr size_t off_sh = NSTAGE * stage_bytes;
   static constexpr size_t off_in = (off_sh + sizeof(typename P::Shared) + 127) & ~(size_t)127;  // ACC input staging
   static constexpr size_t off_bar = off_in + P::IN_BYTES;
-  static constexpr size_t bytes = off_bar + 8 * GPB_COUNT + 32;
+  static constexpr size_t off_sin = (off_bar + 8 * GPB_COUNT + 15) & ~(size_t)15;   // SOLVE input staging: 3 row slots x 8-byte fields x threads
+  static constexpr size_t bytes = off_sin + (size_t)3 * P::SOLVE_FIELDS * GP_SOLVE_THREADS * 8 + 16;
 };
 
 struct GpStage {
@@ -372,8 +374,8 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
       mbar_wait_park(bars + GPB_TFULL + tring.s, tring.ph);
       if (t == 0 && G != 1) GP_STAMP(P, rows_out, 9);
       if (qload && (enter || leave) && !(GP_EXP_SKIP_ACC && yin > g.y_begin + 4)) {
-        const int4* slot = reinterpret_cast<const int4*>(stage_in) + ((size_t)tring.s * 2 * GP_NT + (t - tA)) * P::NP;
-        acc.template accum_staged<G>(slot, slot + (size_t)GP_NT * P::NP, gx >> 2, enter, leave, cmask, Vl);
+        const int4* slot = reinterpret_cast<const int4*>(stage_in) + ((size_t)tring.s * 2 * GP_NTR + (t - tA)) * P::NP;
+        acc.template accum_staged<G>(slot, slot + (size_t)GP_NTR * P::NP, gx >> 2, enter, leave, cmask, Vl);
       }
       mbar_arrive(bars + GPB_TEMPTY + tring.s);
       tring.template next<P::NRING>();
@@ -434,16 +436,16 @@ __device__ __forceinline__ void gp_aux(const GfCommon& gc, const GfGeom& gg, uns
       uint64_t* bar = bars + GPB_TFULL + j;
       if (GP_EXP_SKIP_TMA && yi > g.y_begin + 4) { mbar_arrive_expect_tx(bar, 0u); return; }
       mbar_arrive_expect_tx(bar, ((en ? 1u : 0u) + (le ? 1u : 0u)) * row_bytes);
-      int4* slot = reinterpret_cast<int4*>(smem + L::off_in) + (size_t)j * 2 * GP_NT * P::NP;
+      int4* slot = reinterpret_cast<int4*>(smem + L::off_in) + (size_t)j * 2 * GP_NTR * P::NP;
       const int gqa = (g.xs - g.HL - 4 + 4 * tA) >> 2;   // global quad index of strip quad tA
       const int4* rows = reinterpret_cast<const int4*>(P::coef_rows(gc, blockIdx.z, gg));
       const size_t qpr = (size_t)(g.Wp >> 2);
 #if GP_L2_HINT
       if (en) tma_bulk_g2s_hint(slot, rows + ((size_t)yi * qpr + gqa) * P::NP, row_bytes, bar, pol_enter);
-      if (le) tma_bulk_g2s_hint(slot + (size_t)GP_NT * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, bar, pol_leave);
+      if (le) tma_bulk_g2s_hint(slot + (size_t)GP_NTR * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, bar, pol_leave);
 #else
       if (en) tma_bulk_g2s(slot, rows + ((size_t)yi * qpr + gqa) * P::NP, row_bytes, bar);
-      if (le) tma_bulk_g2s(slot + (size_t)GP_NT * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, bar);
+      if (le) tma_bulk_g2s(slot + (size_t)GP_NTR * P::NP, rows + ((size_t)yli * qpr + gqa) * P::NP, row_bytes, bar);
 #endif
     }
   };
@@ -561,7 +563,21 @@ __device__ __forceinline__ void gp_solve(const GfCommon& gc, const GfGeom& gg, u
   const int nx1 = max(min(gx + 1 + g.r, g.W - 1) - max(gx + 1 - g.r, 0) + 1, 1);
   Solve sol;
   sol.init(gc, blockIdx.z, reinterpret_cast<typename P::Shared*>(smem + L::off_sh), gg);
-  if (act) sol.row_prefetch(g.ys, gx);
+  // policies with SOLVE_FIELDS > 0: the per-pixel inputs of SOLVE (packed guide, J) are requested two rows ahead - one row
+  // (about 1 us) did not cover the DRAM latency under load: a fifth of the SOLVE samples of GF2b waited on the first use of
+  // the prefetched word.  They land in this thread's own slots of a three-row staging ring in shared memory (cp.async): no
+  // register is tied to a load in flight, and no barrier is needed (the thread reads back only what it requested itself)
+  unsigned char* sin = smem + L::off_sin + (size_t)v * 8;
+  constexpr int SLOT = P::SOLVE_FIELDS * GP_SOLVE_THREADS * 8;
+  if constexpr (P::SOLVE_FIELDS > 0) {
+    if (act) sol.row_prefetch(g.ys, gx, sin);
+    cp_async_commit();
+    if (act && g.ys + 1 < g.ye) sol.row_prefetch(g.ys + 1, gx, sin + SLOT);
+    cp_async_commit();
+  } else {
+    if (act) sol.row_prefetch(g.ys, gx, nullptr);   // register prefetch, one row ahead
+  }
+  int slot = 0;
   GpRing ring;
   // All eight warps work on the same row.  Two alternatives were built and measured slower (profiles/r2_summary.md): the
   // window sums of the next row requested before the per-pixel work of this one (software pipeline over rows), and two
@@ -576,8 +592,17 @@ __device__ __forceinline__ void gp_solve(const GfCommon& gc, const GfGeom& gg, u
     if (v == 0) GP_STAMP(P, yo - g.ys, 6);
     ring.template next<NSTAGE>();
     if (act && !(GP_EXP_SKIP_SOLVE && yo > g.ys)) {
-      sol.row_pickup();
-      if (yo + 1 < g.ye) sol.row_prefetch(yo + 1, gx);
+      if constexpr (P::SOLVE_FIELDS > 0) {
+        const int s2 = slot >= 1 ? slot - 1 : 2;   // (slot + 2) % 3
+        if (yo + 2 < g.ye) sol.row_prefetch(yo + 2, gx, sin + s2 * SLOT);
+        cp_async_commit();
+        cp_async_wait_2();
+        sol.row_pickup(sin + slot * SLOT);
+        slot = slot == 2 ? 0 : slot + 1;
+      } else {
+        sol.row_pickup(nullptr);
+        if (yo + 1 < g.ye) sol.row_prefetch(yo + 1, gx, nullptr);
+      }
       const int ny = min(yo + g.r, g.H - 1) - max(yo - g.r, 0) + 1;
       // both pixels in straight-line code (no branch between them: the scheduler interleaves the two dependent chains);
       // the second one is a pad column only in the last pair of an odd-width image: computed, not stored / reduced
@@ -682,6 +707,7 @@ struct PipGF1a {
   static constexpr bool PLANE_READER = false;
   static constexpr int NDA = 2;
   static constexpr int IN_BYTES = GP_NGRP == 1 ? 4 * GP_NT * 20 : 0;   // per worker: 4 cp.async slots (2 buffers x enter / leave) of one uint4 + one u32
+  static constexpr int SOLVE_FIELDS = 0;   // 8-byte words of per-pixel-pair input SOLVE reads per row (staged by cp.async)
   struct Shared {
     double pT[2][256];    // rint(p_c * 2^28) as a function of the window-min k' (an exact integer-valued double)
     FrameConst fc;
@@ -772,8 +798,8 @@ struct PipGF1a {
       sh = s; Wp = gg.Wp;
       ab = reinterpret_cast<GP_COEF_T*>(g.ab) + (size_t)f * 8 * (size_t)gg.Wp * gg.H;
     }
-    __device__ __forceinline__ void row_prefetch(int, int) {}
-    __device__ __forceinline__ void row_pickup() {}
+    __device__ __forceinline__ void row_prefetch(int, int, unsigned char*) {}
+    __device__ __forceinline__ void row_pickup(const unsigned char*) {}
     // results go out pixel by pixel: two 16-byte chunks (one per filter) into the swizzled quad block
     __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
       const double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
@@ -804,6 +830,7 @@ struct PipGF2a {
   static constexpr bool PLANE_READER = false;
   static constexpr int NDA = 1;
   static constexpr int IN_BYTES = GP_NGRP == 1 ? 4 * GP_NT * 32 : 0;
+  static constexpr int SOLVE_FIELDS = 0;   // 8-byte words of per-pixel-pair input SOLVE reads per row (staged by cp.async)
   struct Shared { FrameConst fc; double epsN_k, pinv; CoefScale cs; };
   static __device__ void init_shared(const GfCommon& g, int f, Shared* sh, const GfGeom& gg) {
     if (threadIdx.x == 0) {
@@ -872,8 +899,8 @@ struct PipGF2a {
       sh = s; Wp = gg.Wp;
       ab = reinterpret_cast<GP_COEF_T*>(g.ab) + (size_t)f * 8 * (size_t)gg.Wp * gg.H;
     }
-    __device__ __forceinline__ void row_prefetch(int, int) {}
-    __device__ __forceinline__ void row_pickup() {}
+    __device__ __forceinline__ void row_prefetch(int, int, unsigned char*) {}
+    __device__ __forceinline__ void row_pickup(const unsigned char*) {}
     __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
       const double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
       double M[6], Sd[3], A[6], rdet, a[3], b;
@@ -942,7 +969,8 @@ struct PipGF1b {
   static constexpr int NI = 0, ND = 8, NP = 8, NSTAGE = 2, NRING = 3, ACC_REGS = GP_B_ACC_REGS, SOLVE_REGS = GP_SOLVE_REGS_FOR(GP_B_ACC_REGS);
   static constexpr bool PLANE_READER = true;
   static constexpr int NDA = 4;   // group 0: the blue filter's sums, group 1: the green filter's
-  static constexpr int IN_BYTES = NRING * 2 * GP_NT * NP * 16;   // ring slots x (entering, leaving) row
+  static constexpr int IN_BYTES = NRING * 2 * GP_NTR * NP * 16;   // ring slots x (entering, leaving) row
+  static constexpr int SOLVE_FIELDS = 0;   // the one word per row stays a register prefetch (the staged copy measured 5 % slower here)
   struct Shared {
     double nrm[256];
     FrameConst fc;
@@ -987,8 +1015,8 @@ struct PipGF1b {
       cnt = 0; rmn = 255; rmx = 0; rsum = 0; nanf = 0;
       o[0][0] = o[0][1] = o[1][0] = o[1][1] = 0.f;
     }
-    __device__ __forceinline__ void row_prefetch(int y, int x) { knext = __ldg(reinterpret_cast<const uint2*>(kq + (size_t)y * Wp + x)); }
-    __device__ __forceinline__ void row_pickup() { kcur = knext; }
+    __device__ __forceinline__ void row_prefetch(int y, int x, unsigned char*) { knext = __ldg(reinterpret_cast<const uint2*>(kq + (size_t)y * Wp + x)); }
+    __device__ __forceinline__ void row_pickup(const unsigned char*) { kcur = knext; }
     __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd, bool valid) {
       const double invN = rcp_fast(u2d((uint32_t)Ncnt));
       const uint32_t w = cc ? kcur.y : kcur.x;
@@ -1055,7 +1083,8 @@ struct PipGF2b {
   static constexpr int NI = 0, ND = 4, NP = 4, NSTAGE = 3, NRING = 4, ACC_REGS = GP_B_ACC_REGS, SOLVE_REGS = GP_SOLVE_REGS_FOR(GP_B_ACC_REGS);
   static constexpr bool PLANE_READER = true;
   static constexpr int NDA = 2;
-  static constexpr int IN_BYTES = NRING * 2 * GP_NT * NP * 16;
+  static constexpr int IN_BYTES = NRING * 2 * GP_NTR * NP * 16;
+  static constexpr int SOLVE_FIELDS = 4;   // 8-byte words of per-pixel-pair input SOLVE reads per row (staged by cp.async)
   struct Shared { ExpShared e; CoefScale cs; };
   static __device__ void init_shared(const GfCommon& g, int f, Shared* sh, const GfGeom& gg) {
     exp_shared_init(&sh->e, g.fs[f], (double)gg.W * (double)gg.H);
@@ -1079,7 +1108,7 @@ struct PipGF2b {
     const Shared* sh; GfCommon g; int Wp, H, f;
     const uint32_t* kq; const uint32_t* ycc; const float* J; float* refS;
     double omn, omx; unsigned nanf;
-    uint2 kn, yn, kc, yc; float2 jbn, jgn, jbc, jgc;
+    uint2 kc, yc; float2 jbc, jgc;
     float o[2];
     __device__ __forceinline__ void init(const GfCommon& gc, int frame, Shared* s, const GfGeom& gg) {
       g = gc; sh = s; Wp = gg.Wp; H = gg.H; f = frame;
@@ -1091,14 +1120,18 @@ struct PipGF2b {
       omn = __longlong_as_double(0x7ff0000000000000ll); omx = -omn; nanf = 0;
       o[0] = o[1] = 0.f;
     }
-    __device__ __forceinline__ void row_prefetch(int y, int x) {
+    static constexpr int FLD = GP_SOLVE_THREADS * 8;   // field pitch of a staging slot
+    __device__ __forceinline__ void row_prefetch(int y, int x, unsigned char* st) {
       const size_t n_pp = (size_t)Wp * H, p = (size_t)y * Wp + x;
-      kn = __ldg(reinterpret_cast<const uint2*>(kq + p));
-      yn = __ldg(reinterpret_cast<const uint2*>(ycc + p));
-      jbn = __ldg(reinterpret_cast<const float2*>(J + p));
-      jgn = __ldg(reinterpret_cast<const float2*>(J + n_pp + p));
+      cp_async8(st, kq + p);
+      cp_async8(st + FLD, ycc + p);
+      cp_async8(st + 2 * FLD, J + p);
+      cp_async8(st + 3 * FLD, J + n_pp + p);
     }
-    __device__ __forceinline__ void row_pickup() { kc = kn; yc = yn; jbc = jbn; jgc = jgn; }
+    __device__ __forceinline__ void row_pickup(const unsigned char* st) {
+      kc = *reinterpret_cast<const uint2*>(st); yc = *reinterpret_cast<const uint2*>(st + FLD);
+      jbc = *reinterpret_cast<const float2*>(st + 2 * FLD); jgc = *reinterpret_cast<const float2*>(st + 3 * FLD);
+    }
     __device__ __forceinline__ void column(int cc, int, int, int Ncnt, const uint32_t*, const double* sd, bool valid) {
       const double invN = rcp_fast(u2d((uint32_t)Ncnt));
       const uint32_t yw = cc ? yc.y : yc.x;
@@ -1148,7 +1181,8 @@ struct PipGFq {
   static constexpr int NI = 0, ND = 4, NP = 4, NSTAGE = 3, NRING = 4, ACC_REGS = GP_B_ACC_REGS, SOLVE_REGS = GP_SOLVE_REGS_FOR(GP_B_ACC_REGS);
   static constexpr bool PLANE_READER = true;
   static constexpr int NDA = 2;
-  static constexpr int IN_BYTES = NRING * 2 * GP_NT * NP * 16;
+  static constexpr int IN_BYTES = NRING * 2 * GP_NTR * NP * 16;
+  static constexpr int SOLVE_FIELDS = 1;   // 8-byte words of per-pixel-pair input SOLVE reads per row (staged by cp.async)
   struct Shared { FrameConst fc; CoefScale cs; };
   static __device__ void init_shared(const GfCommon& g, int f, Shared* sh, const GfGeom&) {
     if (threadIdx.x == 0) { load_frame_const(g.fs[f], sh->fc); sh->cs = coef_scale(g.eps, (double)sh->fc.yi_rng); }
@@ -1170,14 +1204,14 @@ struct PipGFq {
   struct Solve {
     const Shared* sh; int W, Wp;
     const uint32_t* ycc; double* q_out;
-    uint2 yn, yc;
+    uint2 yc;
     __device__ __forceinline__ void init(const GfCommon& g, int f, Shared* s, const GfGeom& gg) {
       sh = s; W = gg.W; Wp = gg.Wp;
       ycc = g.ycc + (size_t)f * (size_t)gg.Wp * gg.H;
       q_out = g.dbg_tref + (size_t)f * (size_t)gg.W * gg.H;
     }
-    __device__ __forceinline__ void row_prefetch(int y, int x) { yn = __ldg(reinterpret_cast<const uint2*>(ycc + (size_t)y * Wp + x)); }
-    __device__ __forceinline__ void row_pickup() { yc = yn; }
+    __device__ __forceinline__ void row_prefetch(int y, int x, unsigned char* st) { cp_async8(st, ycc + (size_t)y * Wp + x); }
+    __device__ __forceinline__ void row_pickup(const unsigned char* st) { yc = *reinterpret_cast<const uint2*>(st); }
     __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t*, const double* sd, bool valid) {
       const double invN = rcp_fast(u2d((uint32_t)Ncnt));
       const uint32_t yw = cc ? yc.y : yc.x;
