@@ -6,10 +6,7 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "w_g2a144": ["-DGP_GF2A_ACC_REGS=144"],
-    "narrow": ["-DGP_NARROW=1"],
-    "narrow_g2a152": ["-DGP_NARROW=1", "-DGP_GF2A_ACC_REGS=152"],
-    "narrow_g2a136": ["-DGP_NARROW=1", "-DGP_GF2A_ACC_REGS=136"],
+    "trace": ["-DGP_TRACE=1"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 

@@ -229,8 +229,8 @@ __device__ __forceinline__ void win15(const uint32_t (&p)[M], uint32_t (&o)[N]) 
   for (int i = 0; i < N; i++) o[i] = MAX ? __vmaxu2(b[i], b[i + 6]) : __vminu2(b[i], b[i + 6]);
 }
 
-__device__ __forceinline__ void wf_cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+__device__ __forceinline__ void wf_cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
 // rows of one vertical run: packs (B', G', R', min_B') and min_G' of every pixel (main.py:17's k' = k - kmin) and returns the
@@ -297,17 +297,17 @@ __global__ void __launch_bounds__(256, WF_CTAS) window15_kernel(const uint8_t* _
   // words into a raw staging area that borrows HX0 (free until the horizontal phase), then get unpacked from shared
   uint32_t* RAW = HX0;  // [WF_RH][64] words
   const bool words = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);  // rows start on 4-byte boundaries
-  if (words && x0 >= WF_RB && x0 - WF_RB + 80 <= W) {
-    // no column clamp: 60 words per row, a warp per row, then four pixels (three words) per unpack task
-    const uint32_t* col = reinterpret_cast<const uint32_t*>(img + (size_t)(x0 - WF_RB) * 3);
+  const bool dwords = ((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(img) & 7) == 0);  // ... and the region rows of a tile on 8-byte ones
+  if (dwords && x0 >= WF_RB && x0 - WF_RB + 80 <= W) {
+    // no column clamp: the 240 bytes of a row are 30 aligned 8-byte copies (x0 * 3 - 24 is a multiple of 8), a warp per
+    // row, then four pixels (three words) per unpack task
+    const uint2* col = reinterpret_cast<const uint2*>(img + (size_t)(x0 - WF_RB) * 3);
 #pragma unroll
     for (int k = 0; k < (WF_RH + 7) / 8; k++) {
       const int ry = warp + 8 * k;
-      if (ry < WF_RH) {
+      if (ry < WF_RH && lane < 30) {
         const int y = min(max(y0 - WF_R + ry, 0), H - 1);
-        const uint32_t* row = col + (size_t)y * (W * 3 / 4);
-        wf_cp_async4(RAW + ry * 64 + lane, row + lane);
-        if (lane < 28) wf_cp_async4(RAW + ry * 64 + 32 + lane, row + 32 + lane);
+        wf_cp_async8(reinterpret_cast<uint2*>(RAW + ry * 64) + lane, col + (size_t)y * (W * 3 / 8) + lane);
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");

@@ -686,6 +686,18 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gp_kernel(GfCommon gc, GfGeom g
 // ------------------------------------------------------------------------------------------------
 // policies
 // ------------------------------------------------------------------------------------------------
+// 1 / (pixels in the window) of the two pixels of a SOLVE thread: the count changes only in the first and last r rows of the
+// image, so the a-kernels keep the reciprocal (MUFU seed + two Newton steps) from row to row (in the plane readers the
+// branch costs more than it saves: it breaks the straight-line interleave of the two pixels)
+struct GpInvN {
+  int n[2]; double inv[2];
+  __device__ __forceinline__ GpInvN() { n[0] = n[1] = 0; inv[0] = inv[1] = 0.0; }
+  __device__ __forceinline__ double get(int cc, int Ncnt) {
+    if (Ncnt != n[cc]) { n[cc] = Ncnt; inv[cc] = rcp_fast(u2d((uint32_t)Ncnt)); }
+    return inv[cc];
+  }
+};
+
 // 3x3 symmetric solve for one right-hand side; the signal sums carry the 2^pbits scale of the fixed-point signal,
 // rdetP = pinv / det(M) takes it out of a, the product with pinv = 2^-pbits out of b.
 __device__ __forceinline__ void gp_solve_rhs(const double* A, double rdetP, const double* Sd, double N, double invN, double pinv, double Sp,
@@ -794,6 +806,7 @@ struct PipGF1a {
   };
   struct Solve {
     const Shared* sh; int Wp; GP_COEF_T* ab;
+    GpInvN cinv;
     __device__ __forceinline__ void init(const GfCommon& g, int f, Shared* s, const GfGeom& gg) {
       sh = s; Wp = gg.Wp;
       ab = reinterpret_cast<GP_COEF_T*>(g.ab) + (size_t)f * 8 * (size_t)gg.Wp * gg.H;
@@ -801,8 +814,8 @@ struct PipGF1a {
     __device__ __forceinline__ void row_prefetch(int, int, unsigned char*) {}
     __device__ __forceinline__ void row_pickup(const unsigned char*) {}
     // results go out pixel by pixel: two 16-byte chunks (one per filter) into the swizzled quad block
-    __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
-      const double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
+    __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
+      const double N = u2d((uint32_t)Ncnt), invN = cinv.get(cc, Ncnt);
       double M[6], Sd[3], A[6], rdet;
       gf_build_M(si, N, sh->epsN_k * N * N, M, Sd);
       gf_adjugate(M, A, rdet);
@@ -895,14 +908,15 @@ struct PipGF2a {
   };
   struct Solve {
     const Shared* sh; int Wp; GP_COEF_T* ab;
+    GpInvN cinv;
     __device__ __forceinline__ void init(const GfCommon& g, int f, Shared* s, const GfGeom& gg) {
       sh = s; Wp = gg.Wp;
       ab = reinterpret_cast<GP_COEF_T*>(g.ab) + (size_t)f * 8 * (size_t)gg.Wp * gg.H;
     }
     __device__ __forceinline__ void row_prefetch(int, int, unsigned char*) {}
     __device__ __forceinline__ void row_pickup(const unsigned char*) {}
-    __device__ __forceinline__ void column(int, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
-      const double N = u2d((uint32_t)Ncnt), invN = rcp_fast(N);
+    __device__ __forceinline__ void column(int cc, int y, int x, int Ncnt, const uint32_t* si, const double* sd, bool valid) {
+      const double N = u2d((uint32_t)Ncnt), invN = cinv.get(cc, Ncnt);
       double M[6], Sd[3], A[6], rdet, a[3], b;
       gf_build_M(si, N, sh->epsN_k * N * N, M, Sd);
       gf_adjugate(M, A, rdet);
