@@ -6,7 +6,9 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "trace": ["-DGP_TRACE=1"],
+    "ew4": [],
+    "ew3": ["-DDZ_EW_CTAS=3"],
+    "ew2": ["-DDZ_EW_CTAS=2"],
 }
 OUT = os.path.join(ROOT, "scratch", "variants")
 
@@ -31,7 +33,7 @@ def run():
                            capture_output=True, text=True, env=env)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
-            print(name, "fps %.1f" % d["value"], {k: round(v["ms_per_step"], 2) for k, v in d["kernels"].items() if k.startswith("dz_gf")}, flush=True)
+            print(name, "fps %.1f" % d["value"], {k: round(v["ms_per_step"], 2) for k, v in d["kernels"].items() if k.startswith("dz_")}, flush=True)
         except Exception as e:
             print(name, "FAILED", r.stderr[-500:], flush=True)
 

@@ -569,13 +569,15 @@ static int32_t* flags_get(uwip_ctx* ctx, int n) {
   return f;
 }
 
-// sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 512 KB table); keep it below ~48 GB of the
-// 180 GB and split the batch into equal parts so that no part ends up much smaller than the others
-static int sub_batch(int n, int w, int h) {
+// sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 512 KB table); keep it below 80 GB of the 180 GB
+// (UWIP_WORKSPACE_GB overrides), and among the sizes that do take the one that wastes the fewest CTA waves of the marches
+// (dehaze_sub_batch)
+static int sub_batch(const uwip_ctx* ctx, int n, int w, int h) {
   size_t per_frame = (size_t)w * h * 60 + (512u << 10);
-  size_t cap = std::max<size_t>(1, (size_t)48e9 / per_frame);
-  size_t parts = ((size_t)n + cap - 1) / cap;
-  return (int)(((size_t)n + parts - 1) / parts);
+  double gb = 80.0;
+  if (const char* e = getenv("UWIP_WORKSPACE_GB")) { double v = atof(e); if (v >= 1.0) gb = v; }
+  size_t cap = std::max<size_t>(1, (size_t)(gb * 1e9) / per_frame);
+  return dehaze_sub_batch(ctx, n, w, (int)std::min<size_t>(cap, (size_t)n));
 }
 
 int uwip_bgdehaze_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, const uwip_dehaze_params* pp) {
@@ -583,7 +585,7 @@ int uwip_bgdehaze_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, 
   UWIP_REQUIRE(ctx, d_src && d_dst && n > 0, "bad argument");
   uwip_dehaze_params p;
   if (pp) p = *pp; else uwip_dehaze_defaults(&p);
-  int nb = sub_batch(n, w, h);
+  int nb = sub_batch(ctx, n, w, h);
   FrameState* fs = frame_state_get(ctx, nb);
   int32_t* flags = flags_get(ctx, n);
   if (!fs || !flags) return UWIP_ERR_NOMEM;
@@ -647,7 +649,7 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
   CTX_GUARD(ctx);
   UWIP_REQUIRE(ctx, d_src && d_dst, "null pointer");
   UWIP_CHECK(chain_check(ctx, p, n, w, h));
-  int nb = sub_batch(n, w, h);
+  int nb = sub_batch(ctx, n, w, h);
   FrameState* fs = frame_state_get(ctx, nb);
   int32_t* flags = flags_get(ctx, n);
   if (!fs || !flags) return UWIP_ERR_NOMEM;
@@ -660,14 +662,14 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
 }
 
 // Sub-batch schedule of the host-buffer chain.  Only the first upload and the last download are not hidden
-// behind compute, so the first and last sub-batches are short; every sub-batch is a multiple of the
-// "wave" u (frames whose guided-filter strips fill the SMs exactly once) so that no launch ends in a
-// nearly empty wave.  PCIe moves a 4K frame about 2.4x faster than the chain processes it, so going from
-// u to 2u never starves the compute stream.
-static std::vector<int> e2e_schedule(int n, int nb_max, int u) {
+// behind compute, so the first and last sub-batches are short (u frames: one wave of the wide marches); the ones in
+// between take `big` frames = two waves (4K: 37 frames).  At 4K the PCIe link needs about as long for a frame (both
+// directions at once) as the chain does: with four-wave sub-batches (74 frames) the copies no longer hid behind the
+// compute of the sub-batch before and the end-to-end rate fell from 1,004 to 937 frames/s.
+static std::vector<int> e2e_schedule(int n, int nb_max, int u, int big) {
   std::vector<int> sizes;
   u = std::max(1, std::min(u, nb_max));
-  int big = std::max(u, std::min(2 * u, nb_max) / u * u);
+  big = std::max(u, std::min(big, nb_max));
   int rem = n;
   if (rem > 0) { int m = std::min(u, rem); sizes.push_back(m); rem -= m; }
   while (rem > big + u) { sizes.push_back(big); rem -= big; }
@@ -681,9 +683,9 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   CTX_GUARD(ctx);
   UWIP_REQUIRE(ctx, src && dst, "null pointer");
   UWIP_CHECK(chain_check(ctx, p, n, w, h));
-  int nb = sub_batch(n, w, h);
+  int nb = sub_batch(ctx, n, w, h);
   nb = std::max(1, std::min(nb, (n + 1) / 2));  // at least two sub-batches so copies overlap compute
-  std::vector<int> sizes = e2e_schedule(n, nb, dehaze_wave_frames(ctx, w));
+  std::vector<int> sizes = e2e_schedule(n, nb, dehaze_wave_frames(ctx, w), 2 * ctx->sm_count / std::max(1, dehaze_strips(w)));
   nb = *std::max_element(sizes.begin(), sizes.end());
   FrameState* fs = frame_state_get(ctx, nb);
   int32_t* flags = flags_get(ctx, n);

@@ -52,6 +52,7 @@ FrameState* frame_state_get(uwip_ctx* ctx, int n) { return (FrameState*)uwip_slo
 #include "gfmarch.cuh"
 
 int dehaze_gf1a_launch(uwip_ctx* ctx, const GfCommon& gc, int n, int W, int H, int r);   // dehaze_gf1a.cu (narrow strips)
+int dehaze_gf1a_strips(int w);                                                               // strips of a frame in that layout
 
 // ------------------------------------------------------------------------------------------------
 // D0: joint min / max over all channels (bgdehaze/main.py:17)
@@ -530,7 +531,10 @@ __global__ void traw_kernel(const uint32_t* __restrict__ kq, const uint8_t* __re
 // -------------------------------------------------------------------------------------------------
 // E: restored -> R8, I8 -> YCrCb joint min / max (BGDehaze.py:75-80); stores (Yi, Cri, Cbi, Yj)
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) exposure_minmax_kernel(GfCommon g, int W, int H, int Wp, double* dbg_restored) {
+#ifndef DZ_EW_CTAS
+#define DZ_EW_CTAS 4   // resident CTAs per SM of the two element-wise fp64 kernels
+#endif
+__global__ void __launch_bounds__(256, DZ_EW_CTAS) exposure_minmax_kernel(GfCommon g, int W, int H, int Wp, double* dbg_restored) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
@@ -621,7 +625,7 @@ __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) 
 }
 
 // final: (OutputExp - min)/(max - min) * 255 -> rint -> saturate (BGDehaze.py:88-89, main.py:19)
-__global__ void __launch_bounds__(256, 4) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256, DZ_EW_CTAS) final_kernel(GfCommon g, int W, int H, int Wp, uint8_t* __restrict__ dst, double* dbg_out, int32_t* __restrict__ flags) {
   __shared__ ExpShared sh;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
@@ -681,6 +685,32 @@ __global__ void __launch_bounds__(256, 4) final_kernel(GfCommon g, int W, int H,
 int dehaze_wave_frames(const uwip_ctx* ctx, int w) {
   GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
   return std::max(1, ctx->sm_count / cdiv(w, g.SW));
+}
+int dehaze_strips(int w) {
+  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
+  return cdiv(w, g.SW);
+}
+// Sub-batch size of a device-resident batch of n frames when at most `cap` frames of workspace are wanted: the marches run
+// one CTA per SM and strip for the whole height of a frame, so a launch costs ceil(frames * strips / SMs) CTA durations
+// whatever the fill of its last wave.  Among the sizes in [cap/2, cap] take the one whose parts (k - 1 of that size and
+// the remainder) need the fewest waves in total; ties go to the larger size.  (4K, 256 frames, cap 96: 92 + 92 + 72 frames =
+// 14 waves of the wide layout; three equal parts of 86 are 15.)
+int dehaze_sub_batch(const uwip_ctx* ctx, int n, int w, int cap) {
+  cap = std::max(1, cap);
+  if (n <= cap) return n;
+  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
+  const long long sw = cdiv(w, g.SW), sn = dehaze_gf1a_strips(w), sms = std::max(1, ctx->sm_count);
+  // a CTA of a layout with S strips lasts ~1/S of the layout's time per frame; GF1a (narrow strips) is about 0.36 of the
+  // march time of a frame, the three wide marches 0.64
+  auto waves = [&](long long frames, long long strips) { return (double)((frames * strips + sms - 1) / sms) / (double)strips; };
+  double best_cost = -1.0;
+  int best = cap;
+  for (int m = cap; m >= std::max(1, cap / 2); m--) {
+    const int full = n / m, rem = n - full * m;
+    double cost = full * (0.64 * waves(m, sw) + 0.36 * waves(m, sn)) + (rem ? 0.64 * waves(rem, sw) + 0.36 * waves(rem, sn) : 0.0);
+    if (best_cost < 0.0 || cost < best_cost - 1e-9) { best_cost = cost; best = m; }
+  }
+  return best;
 }
 
 int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int W, int H, const uwip_dehaze_params& p,

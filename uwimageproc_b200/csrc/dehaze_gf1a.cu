@@ -10,3 +10,8 @@
 int dehaze_gf1a_launch(uwip_ctx* ctx, const GfCommon& gc, int n, int W, int H, int r) {
   return gp_launch<PipGF1a>(ctx, "dz_gf1a", FUNC_GF1A, gc, n, W, H, r);
 }
+
+int dehaze_gf1a_strips(int w) {
+  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
+  return cdiv(w, g.SW);
+}
