@@ -228,7 +228,10 @@ template <class P>
 struct GpSmem {
   static constexpr int NT = GP_NT, GP = GP_GP, NI = P::NI, ND = P::ND, NSTAGE = P::NSTAGE;
   // one published row: Pd [ND][NT] 4 x f64 (inclusive in-quad prefixes) | Gd [ND][GP] f64 | Pi [NI][NT] uint4 | Gi [NI][GP] u32
-  static constexpr size_t off_gd = (size_t)ND * NT * 32;
+  // (Pd = two arrays: Pa [ND][NT] (p0, p1) and, 64 bytes past a multiple of 128 further, Pb [ND][NT] (p2, p3): consecutive
+  // threads publish consecutive 16 bytes, and the 16-byte loads of the two halves of a quad fall into different banks)
+  static constexpr size_t off_pb = (((size_t)ND * NT * 16 + 127) & ~(size_t)127) + 64;
+  static constexpr size_t off_gd = (off_pb + (size_t)ND * NT * 16 + 127) & ~(size_t)127;
   static constexpr size_t off_pi = off_gd + (size_t)ND * GP * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t stage_bytes = (off_gi + (size_t)NI * GP * 4 + 127) & ~(size_t)127;
@@ -240,14 +243,15 @@ struct GpSmem {
 };
 
 struct GpStage {
-  double2* Pd; double* Gd; uint4* Pi; uint32_t* Gi;   // Pd: two double2 per quad and moment: (p0, p1), (p2, p3 = quad total)
+  double2* Pa; double2* Pb; double* Gd; uint4* Pi; uint32_t* Gi;   // in-quad prefixes per quad and moment: Pa = (p0, p1), Pb = (p2, p3 = quad total)
 };
 template <class P>
 __device__ __forceinline__ GpStage gp_stage(unsigned char* smem, int s) {
   typedef GpSmem<P> L;
   unsigned char* b = smem + (size_t)s * L::stage_bytes;
   GpStage g;
-  g.Pd = reinterpret_cast<double2*>(b);
+  g.Pa = reinterpret_cast<double2*>(b);
+  g.Pb = reinterpret_cast<double2*>(b + L::off_pb);
   g.Gd = reinterpret_cast<double*>(b + L::off_gd);
   g.Pi = reinterpret_cast<uint4*>(b + L::off_pi);
   g.Gi = reinterpret_cast<uint32_t*>(b + L::off_gi);
@@ -399,8 +403,8 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
         for (int k = (G == 1 ? P::NDA : 0); k < (G == 0 ? P::NDA : ND); k++) {
           const double p0 = Acc::to_double(Vl[0][k]), p1 = p0 + Acc::to_double(Vl[1][k]), p2 = p1 + Acc::to_double(Vl[2][k]),
                        p3 = p2 + Acc::to_double(Vl[3][k]);
-          st.Pd[(k * NT + t) * 2] = make_double2(p0, p1);
-          st.Pd[(k * NT + t) * 2 + 1] = make_double2(p2, p3);
+          st.Pa[k * NT + t] = make_double2(p0, p1);
+          st.Pb[k * NT + t] = make_double2(p2, p3);
           st.Gd[k * GP + t] = p3;
         }
       }
@@ -508,20 +512,20 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
     // one 16-byte load, p_tlo[2h] one 8-byte load, and p_tlo[2h-1] is p_tlo[1] for h = 1 and element 0 of quad 0 - the zero
     // guard of every moment row - for h = 0: the same instructions for both halves, no branch between the moments, all
     // addresses a per-thread base plus a constant (a branch per moment kept the loads of the moments from overlapping)
-    const double* Pd = reinterpret_cast<const double*>(st.Pd);
-    const double2* hi_p = st.Pd + thi * 2 + h;
-    const double* lo1_p = Pd + tlo * 4 + 2 * h;
-    const double* lo0_p = h ? Pd + tlo * 4 + 1 : Pd;
+    const double2* half = h ? st.Pb : st.Pa;   // this half's pairs: (p0, p1) or (p2, p3)
+    const double2* hi_p = half + thi;
+    const double* lo1_p = reinterpret_cast<const double*>(half + tlo);
+    const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pa + tlo) + 1 : reinterpret_cast<const double*>(st.Pa);
 #pragma unroll
     for (int k = 0; k < ND; k++) {
       const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
-      const double2 b = hi_p[k * NT * 2];
-      sd[0][k] = (Wq - lo0_p[k * NT * 4]) + b.x;
-      sd[1][k] = (Wq - lo1_p[k * NT * 4]) + b.y;
+      const double2 b = hi_p[k * NT];
+      sd[0][k] = (Wq - lo0_p[k * NT * 2]) + b.x;
+      sd[1][k] = (Wq - lo1_p[k * NT * 2]) + b.y;
     }
   } else {
     const uint32_t* Pis = reinterpret_cast<const uint32_t*>(st.Pi);
-    const double* Pd = reinterpret_cast<const double*>(st.Pd);
+    const double* Pa = reinterpret_cast<const double*>(st.Pa);
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
       const int z = 4 * tq + 2 * h + cc;
@@ -536,8 +540,8 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       for (int k = 0; k < ND; k++) {
         // prefix element (z&3)-1 of quad z>>2
         const int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-        double pl = (el < 0) ? 0.0 : Pd[(k * NT + (zl >> 2)) * 4 + el];
-        double ph = (eh < 0) ? 0.0 : Pd[(k * NT + (zh >> 2)) * 4 + eh];
+        double pl = (el < 0) ? 0.0 : (el < 2 ? Pa[(k * NT + (zl >> 2)) * 2 + el] : st.Pb[k * NT + (zl >> 2)].x);
+        double ph = (eh < 0) ? 0.0 : (eh < 2 ? Pa[(k * NT + (zh >> 2)) * 2 + eh] : st.Pb[k * NT + (zh >> 2)].x);
         sd[cc][k] = (st.Gd[k * GP + (zh >> 2) - 1] + ph) - (st.Gd[k * GP + (zl >> 2) - 1] + pl);
       }
     }
