@@ -880,6 +880,7 @@ struct PipGF2a {
     }
     __device__ __forceinline__ void stage_issue(unsigned char* st, int s, int y, int gx, int t) const {
       const size_t o = (size_t)y * Wp + gx;
+      // (32 bytes per worker: splitting the two quads into two arrays, 16 bytes apart per worker, measured 2 % slower)
       cp_async16(st + ((size_t)s * GP_NT + t) * 32, ycc + o);
       cp_async16(st + ((size_t)s * GP_NT + t) * 32 + 16, sp + o);
     }
@@ -990,14 +991,16 @@ struct PipGF1b {
   static constexpr int IN_BYTES = NRING * 2 * GP_NTR * NP * 16;   // ring slots x (entering, leaving) row
   static constexpr int SOLVE_FIELDS = 0;   // the one word per row stays a register prefetch (the staged copy measured 5 % slower here)
   struct Shared {
-    double nrm[256];
+    double inv_range;   // I_c = k / range as k * (1 / range): one ulp from the quotient, far inside J's 1e-5 (a 256-entry table of
+                        // the exact quotients cost four bank-conflicted gathers per thread and row)
     FrameConst fc;
     CoefScale cs;
   };
   static __device__ void init_shared(const GfCommon& g, int f, Shared* sh, const GfGeom&) {
-    if (threadIdx.x == 0) { load_frame_const(g.fs[f], sh->fc); sh->cs = coef_scale(g.eps, (double)sh->fc.range); }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->nrm[i] = (double)i / (double)sh->fc.range;
+    if (threadIdx.x == 0) {
+      load_frame_const(g.fs[f], sh->fc); sh->cs = coef_scale(g.eps, (double)sh->fc.range);
+      sh->inv_range = 1.0 / (double)sh->fc.range;   // range 0 (constant frame): inf, and 0 * inf = NaN like 0 / 0
+    }
     __syncthreads();
   }
   static __device__ __forceinline__ const void* coef_rows(const GfCommon& g, int f, const GfGeom& gg) {
@@ -1047,7 +1050,7 @@ struct PipGF1b {
         const double q = (s[0] * kd[0] + s[1] * kd[1] + s[2] * kd[2]) * isa + s[3] * isb;   // guidedfilter.py:100-101
         if (dbg && valid) dbg[(size_t)c * W * H + (size_t)y * W + x] = q;
         const double Bc = sh->fc.B[c];
-        const double Jv = (sh->nrm[k[c]] - Bc) * rcp_fast(q) + Bc;                    // BGDehaze.py:53,55
+        const double Jv = (kd[c] * sh->inv_range - Bc) * rcp_fast(q) + Bc;            // BGDehaze.py:53,55 (I_c = k / range)
         float Jf = (float)Jv;
         o[cc][c] = Jf;
         if (valid) {
