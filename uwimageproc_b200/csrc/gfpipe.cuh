@@ -221,6 +221,11 @@ __device__ __forceinline__ void gp_scan_task(T* row, int seg, bool live) {
   }
 }
 
+// layout of the fp64 in-quad prefixes: even / odd elements per array (six conflict-free 8-byte window loads per moment) for the
+// policies with up to four fp64 moments, pairs per array (five loads, one of them two-way conflicted) for those with eight:
+// measured per kernel (profiles/r2_summary.md)
+#define GP_EVEN_ODD(nd) ((nd) <= 4)
+
 // mbarrier indices (up to four stages / ring slots)
 enum { GPB_FULL = 0, GPB_READY = 4, GPB_EMPTY = 8, GPB_TFULL = 12, GPB_TEMPTY = 16, GPB_COUNT = 20 };
 
@@ -243,7 +248,7 @@ struct GpSmem {
 };
 
 struct GpStage {
-  double2* Pa; double2* Pb; double* Gd; uint4* Pi; uint32_t* Gi;   // in-quad prefixes per quad and moment: Pa = (p0, p1), Pb = (p2, p3 = quad total)
+  double2* Pa; double2* Pb; double* Gd; uint4* Pi; uint32_t* Gi;   // in-quad prefixes per quad and moment: Pa = (p0, p1), Pb = (p2, p3 = quad total); policies with few fp64 moments: (p0, p2), (p1, p3)
 };
 template <class P>
 __device__ __forceinline__ GpStage gp_stage(unsigned char* smem, int s) {
@@ -403,8 +408,13 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
         for (int k = (G == 1 ? P::NDA : 0); k < (G == 0 ? P::NDA : ND); k++) {
           const double p0 = Acc::to_double(Vl[0][k]), p1 = p0 + Acc::to_double(Vl[1][k]), p2 = p1 + Acc::to_double(Vl[2][k]),
                        p3 = p2 + Acc::to_double(Vl[3][k]);
-          st.Pa[k * NT + t] = make_double2(p0, p1);
-          st.Pb[k * NT + t] = make_double2(p2, p3);
+          if constexpr (GP_EVEN_ODD(ND)) {
+            st.Pa[k * NT + t] = make_double2(p0, p2);   // even elements
+            st.Pb[k * NT + t] = make_double2(p1, p3);   // odd elements
+          } else {
+            st.Pa[k * NT + t] = make_double2(p0, p1);
+            st.Pb[k * NT + t] = make_double2(p2, p3);
+          }
           st.Gd[k * GP + t] = p3;
         }
       }
@@ -512,16 +522,33 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
     // one 16-byte load, p_tlo[2h] one 8-byte load, and p_tlo[2h-1] is p_tlo[1] for h = 1 and element 0 of quad 0 - the zero
     // guard of every moment row - for h = 0: the same instructions for both halves, no branch between the moments, all
     // addresses a per-thread base plus a constant (a branch per moment kept the loads of the moments from overlapping)
-    const double2* half = h ? st.Pb : st.Pa;   // this half's pairs: (p0, p1) or (p2, p3)
-    const double2* hi_p = half + thi;
-    const double* lo1_p = reinterpret_cast<const double*>(half + tlo);
-    const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pa + tlo) + 1 : reinterpret_cast<const double*>(st.Pa);
+    if constexpr (GP_EVEN_ODD(ND)) {
+      // Pa holds the even elements (p0, p2) of a quad, Pb the odd ones (p1, p3): element 2h of a quad is Pa[quad] component h, so
+      // the two halves of a quad read consecutive 8 bytes (an 8-byte load at a 16-byte stride is two-way bank conflicted);
+      // six conflict-free 8-byte loads per moment
+      const double* ev = reinterpret_cast<const double*>(st.Pa) + h;
+      const double* od = reinterpret_cast<const double*>(st.Pb) + h;
+      const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pb + tlo) : reinterpret_cast<const double*>(st.Pa);   // p1 of tlo / zero guard
 #pragma unroll
-    for (int k = 0; k < ND; k++) {
-      const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
-      const double2 b = hi_p[k * NT];
-      sd[0][k] = (Wq - lo0_p[k * NT * 2]) + b.x;
-      sd[1][k] = (Wq - lo1_p[k * NT * 2]) + b.y;
+      for (int k = 0; k < ND; k++) {
+        const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
+        sd[0][k] = (Wq - lo0_p[k * NT * 2]) + ev[(k * NT + thi) * 2];
+        sd[1][k] = (Wq - ev[(k * NT + tlo) * 2]) + od[(k * NT + thi) * 2];
+      }
+    } else {
+      // Pa = (p0, p1), Pb = (p2, p3): five loads per moment, the pair of quad thi in one 16-byte load (p_tlo[2h] stays a
+      // two-way conflicted 8-byte load; with eight moments the sixth load instruction costs more than the conflict)
+      const double2* half = h ? st.Pb : st.Pa;
+      const double2* hi_p = half + thi;
+      const double* lo1_p = reinterpret_cast<const double*>(half + tlo);
+      const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pa + tlo) + 1 : reinterpret_cast<const double*>(st.Pa);
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+        const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
+        const double2 b = hi_p[k * NT];
+        sd[0][k] = (Wq - lo0_p[k * NT * 2]) + b.x;
+        sd[1][k] = (Wq - lo1_p[k * NT * 2]) + b.y;
+      }
     }
   } else {
     const uint32_t* Pis = reinterpret_cast<const uint32_t*>(st.Pi);
@@ -540,8 +567,11 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       for (int k = 0; k < ND; k++) {
         // prefix element (z&3)-1 of quad z>>2
         const int el = (zl & 3) - 1, eh = (zh & 3) - 1;
-        double pl = (el < 0) ? 0.0 : (el < 2 ? Pa[(k * NT + (zl >> 2)) * 2 + el] : st.Pb[k * NT + (zl >> 2)].x);
-        double ph = (eh < 0) ? 0.0 : (eh < 2 ? Pa[(k * NT + (zh >> 2)) * 2 + eh] : st.Pb[k * NT + (zh >> 2)].x);
+        // element e of a quad: even / odd layout: array e & 1, component e / 2; pair layout: array e / 2, component e & 1
+        const double* Pb = reinterpret_cast<const double*>(st.Pb);
+        constexpr bool EO = GP_EVEN_ODD(ND);
+        double pl = (el < 0) ? 0.0 : (((EO ? (el & 1) : (el >> 1)) ? Pb : Pa)[(k * NT + (zl >> 2)) * 2 + (EO ? (el >> 1) : (el & 1))]);
+        double ph = (eh < 0) ? 0.0 : (((EO ? (eh & 1) : (eh >> 1)) ? Pb : Pa)[(k * NT + (zh >> 2)) * 2 + (EO ? (eh >> 1) : (eh & 1))]);
         sd[cc][k] = (st.Gd[k * GP + (zh >> 2) - 1] + ph) - (st.Gd[k * GP + (zl >> 2) - 1] + pl);
       }
     }
