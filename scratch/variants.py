@@ -6,19 +6,21 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "ew4": [],
-    "ew3": ["-DDZ_EW_CTAS=3"],
-    "ew2": ["-DDZ_EW_CTAS=2"],
+    "g1a_168": ["-DGP_GF1A_ACC_REGS=168"],
+    "g1a_184": ["-DGP_GF1A_ACC_REGS=184"],
+    "g1a_aux72": ["-DGP_AUX_REGS=72"],
+    "g1a_192": ["-DGP_GF1A_ACC_REGS=192", "-DGP_AUX_REGS=72"],
 }
+VARIANT_SOURCE = "dehaze_gf1a.cu"   # the translation unit the -D switches apply to
 OUT = os.path.join(ROOT, "scratch", "variants")
 
 def build():
     os.makedirs(OUT, exist_ok=True)
     B.build()
-    objs = [os.path.join(B.OBJ, s.replace(".cu", ".o")) for s in B.SOURCES if s != "dehaze.cu"]
+    objs = [os.path.join(B.OBJ, s.replace(".cu", ".o")) for s in B.SOURCES if s != VARIANT_SOURCE]
     for name, flags in VARIANTS.items():
-        obj = os.path.join(OUT, "dehaze_%s.o" % name)
-        r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, "dehaze.cu"), "-o", obj], capture_output=True, text=True)
+        obj = os.path.join(OUT, "var_%s.o" % name)
+        r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, VARIANT_SOURCE), "-o", obj], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
         sp = [l.strip() for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
         lib = os.path.join(OUT, "libuwip_%s.so" % name)
@@ -29,7 +31,7 @@ def build():
 def run():
     for name in VARIANTS:
         env = dict(os.environ, UWIP_LIB=os.path.join(OUT, "libuwip_%s.so" % name))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--frames", "144", "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--frames", "148", "--steps", "2", "--warmup", "3", "--no-e2e", "--no-cpu-baseline"],
                            capture_output=True, text=True, env=env)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])

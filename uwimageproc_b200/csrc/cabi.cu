@@ -570,13 +570,22 @@ static int32_t* flags_get(uwip_ctx* ctx, int n) {
 }
 
 // sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 512 KB table); keep it below 80 GB of the 180 GB
-// (UWIP_WORKSPACE_GB overrides), and among the sizes that do take the one that wastes the fewest CTA waves of the marches
-// (dehaze_sub_batch)
+// (UWIP_WORKSPACE_GB overrides) and below 70 % of what the device has free plus what this context already holds, and among
+// the sizes that fit take the one that wastes the fewest CTA waves of the marches (dehaze_sub_batch)
 static int sub_batch(const uwip_ctx* ctx, int n, int w, int h) {
   size_t per_frame = (size_t)w * h * 60 + (512u << 10);
   double gb = 80.0;
   if (const char* e = getenv("UWIP_WORKSPACE_GB")) { double v = atof(e); if (v >= 1.0) gb = v; }
-  size_t cap = std::max<size_t>(1, (size_t)(gb * 1e9) / per_frame);
+  size_t cap_bytes = (size_t)(gb * 1e9);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    size_t held = 0;
+    for (int i = 0; i < kSlots; i++) held += ctx->slot_bytes[i];
+    cap_bytes = std::min(cap_bytes, (size_t)(0.7 * (double)(free_b + held)));
+  } else {
+    cudaGetLastError();
+  }
+  size_t cap = std::max<size_t>(1, cap_bytes / per_frame);
   return dehaze_sub_batch(ctx, n, w, (int)std::min<size_t>(cap, (size_t)n));
 }
 
