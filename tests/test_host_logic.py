@@ -186,3 +186,34 @@ def test_cli_argument_conventions():
 
     assert histretch.main([]) == 0 and aclahe.main([]) == 0   # help paths need no GPU
     assert bgdehaze_main.get_filenames("/nonexistent") == []
+
+
+def test_e2e_schedule_header(tmp_path):
+    """The sub-batch schedule of uwip_chain_bgr8 (csrc/e2e_schedule.h, plain C++): every schedule adds up to the batch, stays
+    inside the workspace cap, and the 4K / 148-SM / 256-frame one is the measured ramp."""
+    import shutil
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = tmp_path / "sched.cpp"
+    src.write_text(
+        '#include <cstdio>\n#include <cstdlib>\n#include "e2e_schedule.h"\n'
+        "int main(int argc, char** argv) {\n"
+        "  auto v = e2e_schedule(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));\n"
+        '  for (int x : v) printf("%d ", x);\n  printf("\\n");\n  return 0;\n}\n')
+    exe = tmp_path / "sched"
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "uwimageproc_b200", "csrc"), str(src), "-o", str(exe)], check=True)
+
+    def sched(n, nb, sms=148, sw=8, sn=9):
+        out = subprocess.run([str(exe)] + [str(a) for a in (n, nb, sms, sw, sn)], check=True, capture_output=True, text=True).stdout
+        return [int(t) for t in out.split()]
+
+    assert sched(256, 148) == [4, 8, 16, 24, 37, 55, 55, 32, 16, 6, 3]
+    for n in list(range(1, 70)) + [100, 127, 200, 255, 256, 257, 1000, 1024]:
+        for nb in (1, 3, 20, 55, 148):
+            for (sms, sw, sn) in ((148, 8, 9), (148, 1, 1), (132, 4, 5), (148, 40, 44)):
+                v = sched(n, nb, sms, sw, sn)
+                assert sum(v) == n and min(v) >= 1 and max(v) <= nb, (n, nb, sms, sw, sn, v)
+                if n > 1:
+                    assert len(v) >= 2, (n, nb, v)   # at least two sub-batches: a copy overlaps a compute

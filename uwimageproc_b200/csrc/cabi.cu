@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "e2e_schedule.h"
 
 // Every entry point runs on the context's device and puts the caller's current device back when it returns (the library
 // is used next to other CUDA code - torch, OpenCV - whose current device it must not change).
@@ -580,7 +581,7 @@ static int sub_batch(const uwip_ctx* ctx, int n, int w, int h) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
     size_t held = 0;
-    for (int i = 0; i < kSlots; i++) held += ctx->slot_bytes[i];
+    for (int i = 0; i < uwip_ctx::kSlots; i++) held += ctx->slot_bytes[i];
     cap_bytes = std::min(cap_bytes, (size_t)(0.7 * (double)(free_b + held)));
   } else {
     cudaGetLastError();
@@ -670,23 +671,6 @@ int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int
   return UWIP_OK;
 }
 
-// Sub-batch schedule of the host-buffer chain.  Only the first upload and the last download are not hidden
-// behind compute, so the first and last sub-batches are short (u frames: one wave of the wide marches); the ones in
-// between take `big` frames = two waves (4K: 37 frames).  At 4K the PCIe link needs about as long for a frame (both
-// directions at once) as the chain does: with four-wave sub-batches (74 frames) the copies no longer hid behind the
-// compute of the sub-batch before and the end-to-end rate fell from 1,004 to 937 frames/s.
-static std::vector<int> e2e_schedule(int n, int nb_max, int u, int big) {
-  std::vector<int> sizes;
-  u = std::max(1, std::min(u, nb_max));
-  big = std::max(u, std::min(big, nb_max));
-  int rem = n;
-  if (rem > 0) { int m = std::min(u, rem); sizes.push_back(m); rem -= m; }
-  while (rem > big + u) { sizes.push_back(big); rem -= big; }
-  if (rem > u) { sizes.push_back(rem - u); rem = u; }
-  if (rem > 0) sizes.push_back(rem);
-  return sizes;
-}
-
 // host buffers: H2D / compute / D2H pipelined over sub-batches with two staging buffers per direction
 int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int w, int h, const uwip_chain_params* p) {
   CTX_GUARD(ctx);
@@ -694,7 +678,20 @@ int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n, int 
   UWIP_CHECK(chain_check(ctx, p, n, w, h));
   int nb = sub_batch(ctx, n, w, h);
   nb = std::max(1, std::min(nb, (n + 1) / 2));  // at least two sub-batches so copies overlap compute
-  std::vector<int> sizes = e2e_schedule(n, nb, dehaze_wave_frames(ctx, w), 2 * ctx->sm_count / std::max(1, dehaze_strips(w)));
+  std::vector<int> sizes = e2e_schedule(n, nb, ctx->sm_count, dehaze_strips(w), dehaze_strips_narrow(w));
+  if (const char* e = getenv("UWIP_E2E_SIZES")) {   // tuning: an explicit comma-separated schedule (used when it adds up to n)
+    std::vector<int> v;
+    long sum = 0;
+    for (const char* q = e; *q;) {
+      char* end = nullptr;
+      long m = strtol(q, &end, 10);
+      if (end == q || m <= 0) { v.clear(); break; }
+      v.push_back((int)m); sum += m;
+      q = (*end == ',') ? end + 1 : end;
+      if (*end && *end != ',') { v.clear(); break; }
+    }
+    if (!v.empty() && sum == n && *std::max_element(v.begin(), v.end()) <= nb) sizes = v;
+  }
   nb = *std::max_element(sizes.begin(), sizes.end());
   FrameState* fs = frame_state_get(ctx, nb);
   int32_t* flags = flags_get(ctx, n);

@@ -381,8 +381,8 @@ struct DehazeDebug {  // optional float64 stage outputs for the stage-wise host 
 };
 int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n, int w, int h, const uwip_dehaze_params& p, bool minmax_done, FrameState* fs, DehazeDebug* dbg, int32_t* d_flags = nullptr);
 int frame_state_reset(uwip_ctx* ctx, FrameState* fs, int n);
-int dehaze_wave_frames(const uwip_ctx* ctx, int w);  // frames whose guided-filter strips fill the SMs exactly once
-int dehaze_strips(int w);  // strips of a frame in the wide layout of the marches
+int dehaze_strips(int w);         // strips of a frame in the wide layout of the marches (GF1b, GF2a, GF2b)
+int dehaze_strips_narrow(int w);  // ... in the narrow layout (GF1a)
 int dehaze_sub_batch(const uwip_ctx* ctx, int n, int w, int cap);  // sub-batch size <= cap that wastes the fewest CTA waves
 FrameState* frame_state_get(uwip_ctx* ctx, int n);
 int boxfilter_f64_dev(uwip_ctx* ctx, const double* d_src, double* d_tmp, double* d_dst, int w, int h, int r);

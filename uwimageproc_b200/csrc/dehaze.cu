@@ -682,14 +682,12 @@ __global__ void __launch_bounds__(256, DZ_EW_CTAS) final_kernel(GfCommon g, int 
 // -------------------------------------------------------------------------------------------------
 // Batch size for which the strips of the one-CTA-per-SM marches make one full wave (4K: 148 SMs / 5 strips =
 // 29 frames); the host-buffer pipeline cuts its sub-batches in multiples of it.
-int dehaze_wave_frames(const uwip_ctx* ctx, int w) {
-  GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
-  return std::max(1, ctx->sm_count / cdiv(w, g.SW));
-}
+// strips of a frame in the two layouts of the marches (4K: 8 wide, 9 narrow)
 int dehaze_strips(int w) {
   GfGeom g = gf_geometry(w, 4 * 40 + 2, 40);
   return cdiv(w, g.SW);
 }
+int dehaze_strips_narrow(int w) { return dehaze_gf1a_strips(w); }
 // Sub-batch size of a device-resident batch of n frames when at most `cap` frames of workspace are wanted: the marches run
 // one CTA per SM and strip for the whole height of a frame, so a launch costs ceil(frames * strips / SMs) CTA durations
 // whatever the fill of its last wave.  Among the sizes in [cap/2, cap] take the one whose parts (k - 1 of that size and
