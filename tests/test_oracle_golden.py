@@ -221,3 +221,16 @@ def test_parametros_aclahe_k4():
     bs, cl, ent = O.parametros_aclahe(img, "repaired")
     assert np.abs(ent - z["entropies"]).max() < 2e-6
     assert (bs, cl) == tuple(int(v) for v in z["repaired"]) == (4, 7)
+
+
+def test_k3_background_light_full_fixture(kat):
+    """SURVEY K3 on the CPU: the oracle's Background_light (first-index tie rule) on the full-resolution fixture frame shipped
+    by oracle/make_golden_k3.py reproduces the B and indices make_golden.py stored from the reference's decoded image."""
+    z = np.load(os.path.join(GOLD, "k3_pis_full.npz"))
+    for key in z.files:
+        name = key.split("/")[0]
+        img = z[key]
+        assert O.crc32(img) == kat["K3"][name]["decoded_crc"]
+        B, idx = O.background_light(O.normalize_frame(img), 15, True)
+        assert [float(v) for v in B] == kat["K3"][name]["B_first_index"]
+        assert [int(i) for i in idx] == kat["K3"][name]["idx"]
