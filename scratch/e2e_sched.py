@@ -11,13 +11,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W, H = 3840, 2160
 SCHEDULES = {
     "default": None,
-    "D": [4, 6, 10, 16] + [32] * 6 + [16, 8, 4],
-    "S1": [1, 2, 4, 8, 12, 16, 24, 37, 55, 37, 24, 15, 9, 6, 4, 2],
-    "S2": [2, 5, 9, 16, 27, 37, 55, 37, 27, 16, 12, 8, 4, 1],
-    "S3": [3, 6, 10, 16, 24, 37, 55, 49, 32, 16, 6, 2],
-    "S4": [4, 8, 16, 24, 37, 55, 55, 32, 16, 6, 3],
-    "S5": [2, 4, 8, 16, 24, 37, 74, 49, 24, 12, 4, 2],
-    "D2": [4, 6, 10, 16] + [32] * 6 + [16, 8, 4],
+    "flat32": [16] + [32] * 7 + [16],
+    "ramp55": [4, 8, 16, 24, 37, 55, 55, 32, 16, 6, 3],
+    "default2": None,
 }
 ctx = u.Context(0)
 stream = torch.cuda.Stream()

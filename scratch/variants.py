@@ -6,25 +6,29 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "g1a_168": ["-DGP_GF1A_ACC_REGS=168"],
-    "g1a_184": ["-DGP_GF1A_ACC_REGS=184"],
-    "g1a_aux72": ["-DGP_AUX_REGS=72"],
-    "g1a_192": ["-DGP_GF1A_ACC_REGS=192", "-DGP_AUX_REGS=72"],
+    "wq_none": ["-DGP_AUX_WQ=0x0"],
+    "wq_all": ["-DGP_AUX_WQ=0xF"],
+    "wq_a": ["-DGP_AUX_WQ=0x5"],      # GF1a + GF2a
+    "wq_b": ["-DGP_AUX_WQ=0xA"],      # GF1b + GF2b
+    "wq_2a": ["-DGP_AUX_WQ=0x4"],
 }
-VARIANT_SOURCE = "dehaze_gf1a.cu"   # the translation unit the -D switches apply to
+VARIANT_SOURCES = ["dehaze.cu", "dehaze_gf1a.cu"]   # the translation units the -D switches apply to
 OUT = os.path.join(ROOT, "scratch", "variants")
 
 def build():
     os.makedirs(OUT, exist_ok=True)
     B.build()
-    objs = [os.path.join(B.OBJ, s.replace(".cu", ".o")) for s in B.SOURCES if s != VARIANT_SOURCE]
+    objs = [os.path.join(B.OBJ, s.replace(".cu", ".o")) for s in B.SOURCES if s not in VARIANT_SOURCES]
     for name, flags in VARIANTS.items():
-        obj = os.path.join(OUT, "var_%s.o" % name)
-        r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, VARIANT_SOURCE), "-o", obj], capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr[-3000:]
-        sp = [l.strip() for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
+        vobjs, sp = [], []
+        for src in VARIANT_SOURCES:
+            obj = os.path.join(OUT, "var_%s_%s.o" % (name, src.replace(".cu", "")))
+            r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, src), "-o", obj], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            sp += [l.strip() for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores" not in l]
+            vobjs.append(obj)
         lib = os.path.join(OUT, "libuwip_%s.so" % name)
-        r = subprocess.run([B._nvcc(), "-shared", "-o", lib] + objs + [obj, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lnvjpeg_static", "-lculibos", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
+        r = subprocess.run([B._nvcc(), "-shared", "-o", lib] + objs + vobjs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lnvjpeg_static", "-lculibos", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         print(name, flags, "spills:", sp)
 

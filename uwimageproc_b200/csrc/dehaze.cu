@@ -581,27 +581,30 @@ __global__ void __launch_bounds__(256, DZ_EW_CTAS) exposure_minmax_kernel(GfComm
   }
 }
 
-// S (BGDehaze.py:83) as a table over (Yi - min, Yj - min): both are bytes.  grid (256, n), block 256.
-__global__ void __launch_bounds__(256) stab_kernel(const FrameState* __restrict__ fs, double* __restrict__ stab) {
+// S (BGDehaze.py:83) as a table over (Yi - min, Yj - min): both are bytes.  grid (256, n), block 256.  The entry is what the
+// marches consume - rint(min(S, 1.6) 2^28) as a 32-bit integer - or GP_S_NAN where S is 0/0 (a quarter of a megabyte per frame
+// instead of half of one as doubles: the per-pixel gather of splane_kernel hits the caches more often and converts nothing)
+constexpr uint32_t GP_S_NAN = 0xffffffffu;   // above every real entry (1.6 x 2^28 = 0x1999999a)
+__global__ void __launch_bounds__(256) stab_kernel(const FrameState* __restrict__ fs, uint32_t* __restrict__ stab) {
   int f = blockIdx.y, gy = blockIdx.x, j = threadIdx.x;
   const FrameState& s = fs[f];
   double yi_rng = (double)((int)s.yi_max - (int)s.yi_min), yj_rng = (double)((int)s.yj_max - (int)s.yj_min);
   double yi = (double)gy / yi_rng, yj = (double)j / yj_rng;
   double yi2 = 0.3 * (yi * yi);
-  stab[(size_t)f * 65536 + gy * 256 + j] = (yj * yi + yi2) / (yj * yj + yi2);
+  const double S = (yj * yi + yi2) / (yj * yj + yi2);
+  stab[(size_t)f * 65536 + gy * 256 + j] = (S == S) ? __double2uint_rn(fmin(S, GP_S_PMAX) * GP_PSCALE) : GP_S_NAN;
 }
 
 // S per pixel as an f32 plane: GF2a then reads it through the same staged row copies as the guide instead
 // of gathering from the table inside the march (f32 keeps 2^-24 relative: far inside the 1e-5 budget).
 __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) {
-  const double pscale = GP_PSCALE;
   int f = blockIdx.y;
   size_t n_pp = (size_t)Wp * H;
   const FrameState& s = g.fs[f];
   const uint32_t a = s.yi_min, b = s.yj_min;
   const uint32_t ysub = a | (a << 8) | (a << 16) | (b << 24);
   const uint32_t* ycc = g.ycc + (size_t)f * n_pp;
-  const double* stab = g.stab + (size_t)f * 65536;
+  const uint32_t* stab = g.stab + (size_t)f * 65536;
   uint32_t* sp = reinterpret_cast<uint32_t*>(g.splane) + (size_t)f * n_pp;
   const size_t n_q = n_pp / 4;
   bool nan_seen = false;
@@ -612,12 +615,12 @@ __global__ void __launch_bounds__(256) splane_kernel(GfCommon g, int H, int Wp) 
     for (int c = 0; c < 4; c++) {
       uint32_t w = quad_get(yw, c);
       // pad columns hold zeros: keep them away from the table (their S is never used)
-      bool pad = (w & 255u) < a || (w >> 24) < b;
+      const bool pad = (w & 255u) < a || (w >> 24) < b;
       w -= ysub;
       // S = 0/0 where Yi' = Yj' = 0: the NaN reaches every output of the reference -> flag the frame
-      const double S = pad ? 0.0 : __ldg(stab + (((w & 255u) << 8) | (w >> 24)));
-      if (!(S == S)) nan_seen = true;
-      o[c] = (S == S) ? __double2uint_rn(fmin(S, GP_S_PMAX) * pscale) : 0u;
+      const uint32_t S = pad ? 0u : __ldg(stab + (((w & 255u) << 8) | (w >> 24)));
+      if (S == GP_S_NAN) nan_seen = true;
+      o[c] = (S == GP_S_NAN) ? 0u : S;
     }
     reinterpret_cast<uint4*>(sp)[qi] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -731,7 +734,7 @@ int dehaze_frames_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n
   uint32_t* d_kq = (uint32_t*)uwip_slot(ctx, SLOT_KQ, (size_t)n * n_pp * 4);
   uint8_t* d_mg = (uint8_t*)uwip_slot(ctx, SLOT_MPLANES, (size_t)n * n_pp);
   uint32_t* d_ycc = (uint32_t*)uwip_slot(ctx, SLOT_YCC, (size_t)n * n_pp * 4);
-  double* d_stab = (double*)uwip_slot(ctx, SLOT_STAB, (size_t)n * 65536 * 8);
+  uint32_t* d_stab = (uint32_t*)uwip_slot(ctx, SLOT_STAB, (size_t)n * 65536 * 4);
   float* d_sp = (float*)uwip_slot(ctx, SLOT_SPLANE, (size_t)n * n_pp * sizeof(float));
   dim3 gridw(cdiv(Wp, WK_TX), cdiv(H, WK_TY), n);    // generic-window kernel
   dim3 gridf(cdiv(Wp, WF_TX), cdiv(H, WF_TY), n);    // 15x15 kernel

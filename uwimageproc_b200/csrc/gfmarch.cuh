@@ -118,7 +118,7 @@ struct GfCommon {
   const uint32_t* kq;     // [n][H][Wp] packed k'_b k'_g k'_r m'_b
   const uint8_t* mg;      // [n][H][Wp] m'_g
   uint32_t* ycc;          // [n][H][Wp] packed Yi Cri Cbi Yj
-  const double* stab;     // [n][256][256] exposure ratio S(yi', yj')
+  const uint32_t* stab;   // [n][256][256] exposure ratio S(yi', yj') as rint(S 2^28), 0xffffffff where S is 0/0
   float* splane;          // [n][H][Wp] S per pixel (f32)
   float* ab;              // [n][8][H][Wp]
   float* J;               // [n][2][H][Wp]
