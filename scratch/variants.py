@@ -6,11 +6,10 @@ sys.path.insert(0, ROOT)
 from uwimageproc_b200 import build as B
 
 VARIANTS = {
-    "wq_none": ["-DGP_AUX_WQ=0x0"],
-    "wq_all": ["-DGP_AUX_WQ=0xF"],
-    "wq_a": ["-DGP_AUX_WQ=0x5"],      # GF1a + GF2a
-    "wq_b": ["-DGP_AUX_WQ=0xA"],      # GF1b + GF2b
-    "wq_2a": ["-DGP_AUX_WQ=0x4"],
+    "dpad0": ["-DGP_DPAD=0"],
+    "dpad2": ["-DGP_DPAD=2"],
+    "dpad0b": ["-DGP_DPAD=0"],
+    "dpad2b": ["-DGP_DPAD=2"],
 }
 VARIANT_SOURCES = ["dehaze.cu", "dehaze_gf1a.cu"]   # the translation units the -D switches apply to
 OUT = os.path.join(ROOT, "scratch", "variants")

@@ -87,6 +87,15 @@ constexpr int GP_THREADS = GP_ACC_THREADS + GP_SOLVE_THREADS;
 constexpr int GP_MAXSW = 2 * GP_SOLVE_THREADS;   // output columns per strip
 constexpr int GP_NSEG = 8, GP_SEGQ = 20;         // scan: 8 lanes per moment, 20 quads per lane (5 x 16 bytes of u32: odd -> conflict-free)
 constexpr int GP_GP = GP_NSEG * GP_SEGQ;         // pitch of a quad-total row
+// fp64 quad-total rows: a scan segment of 20 doubles is ten 16-byte chunks - an even number, so the eight lanes of a moment
+// would start 2-way bank conflicted (segment stride 160 B = 8 banks x 5: lanes s and s + 4 share banks).  GP_DPAD doubles of
+// padding after every segment make the stride an odd number of chunks: every 16-byte access of the scan is conflict-free.
+#ifndef GP_DPAD
+#define GP_DPAD 2
+#endif
+constexpr int GP_SEGD = GP_SEGQ + GP_DPAD;       // segment stride of an fp64 quad-total row
+constexpr int GP_GPD = GP_NSEG * GP_SEGD;        // pitch of an fp64 quad-total row
+__device__ __forceinline__ int gp_dpos(int t) { return t + GP_DPAD * (t / GP_SEGQ); }   // position of quad t in such a row
 static_assert(GP_GP >= GP_NT && GP_NGRP * GP_NT + 32 * GP_NAUX == GP_ACC_THREADS, "thread layout");
 
 // The filtered signal p (transmission, exposure ratio) is held as rint(p * 2^28): the guided filter amplifies a
@@ -184,7 +193,7 @@ template <class T, class V4>
 __device__ __forceinline__ void gp_scan_task(T* row, int seg, bool live) {
   constexpr int VW = sizeof(V4) / sizeof(T);  // 4 (u32) or 2 (f64)
   constexpr int NG = GP_SEGQ / 4;             // groups of four values
-  T* p = row + seg * GP_SEGQ;
+  T* p = row + seg * (VW == 2 ? GP_SEGD : GP_SEGQ);
   T v[GP_SEGQ];
 #pragma unroll
   for (int i = 0; i < GP_SEGQ; i += VW) {
@@ -237,7 +246,7 @@ struct GpSmem {
   // threads publish consecutive 16 bytes, and the 16-byte loads of the two halves of a quad fall into different banks)
   static constexpr size_t off_pb = (((size_t)ND * NT * 16 + 127) & ~(size_t)127) + 64;
   static constexpr size_t off_gd = (off_pb + (size_t)ND * NT * 16 + 127) & ~(size_t)127;
-  static constexpr size_t off_pi = off_gd + (size_t)ND * GP * 8;
+  static constexpr size_t off_pi = off_gd + (size_t)ND * GP_GPD * 8;
   static constexpr size_t off_gi = off_pi + (size_t)NI * NT * 16;
   static constexpr size_t stage_bytes = (off_gi + (size_t)NI * GP * 4 + 127) & ~(size_t)127;
   static constexpr size_t off_sh = NSTAGE * stage_bytes;
@@ -303,6 +312,7 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
   const GpGeo g = gp_geo(gg);
   const int t = threadIdx.x - GP_SOLVE_THREADS - (G == 1 ? GP_NT : 0);
   const int gx = g.xs - g.HL - 4 + 4 * t;     // image column of this thread's quad (multiple of 4)
+  const int tdp = gp_dpos(t);                 // position of its quad total in an fp64 quad-total row
   const bool qact = t < g.NQ;
   unsigned cmask = 0;                         // columns of the quad that are image columns; quad 0 is the zero guard
   if (qact && t > 0) {
@@ -415,7 +425,7 @@ __device__ __forceinline__ void gp_acc_worker(const GfCommon& gc, const GfGeom& 
             st.Pa[k * NT + t] = make_double2(p0, p1);
             st.Pb[k * NT + t] = make_double2(p2, p3);
           }
-          st.Gd[k * GP + t] = p3;
+          st.Gd[k * GP_GPD + tdp] = p3;
         }
       }
       mbar_arrive(bars + GPB_FULL + ring.s);
@@ -491,7 +501,7 @@ __device__ __forceinline__ void gp_aux(const GfCommon& gc, const GfGeom& gg, uns
     for (int rd = 0; rd < RI + RD; rd++) {
       if (rd % GP_NAUX != aw || (GP_EXP_SKIP_SCAN && yin > g.y_begin + g.r + 3)) continue;
       if (rd < RI) { const int k0 = 4 * rd; gp_scan_task<uint32_t, uint4>(st.Gi + min(k0 + mq, NIa - 1) * GP, seg, k0 + mq < NI); }
-      else { const int k0 = 4 * (rd - RI); gp_scan_task<double, double2>(st.Gd + min(k0 + mq, ND - 1) * GP, seg, k0 + mq < ND); }
+      else { const int k0 = 4 * (rd - RI); gp_scan_task<double, double2>(st.Gd + min(k0 + mq, ND - 1) * GP_GPD, seg, k0 + mq < ND); }
     }
     mbar_arrive(bars + GPB_READY + ring.s);
     if (aw == 0) GP_STAMP(P, yin - g.r - g.ys, 4);
@@ -509,6 +519,7 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
   constexpr int NI = P::NI, ND = P::ND, NT = GP_NT, GP = GP_GP;
   if (g.fast) {
     const int tlo = tq - g.rho, thi = tq + g.rho;
+    const int dhi = gp_dpos(thi - 1), dlo = gp_dpos(tlo - 1);   // loop invariants of the caller's row loop
 #pragma unroll
     for (int k = 0; k < NI; k++) {
       const uint32_t Wq = st.Gi[k * GP + thi - 1] - st.Gi[k * GP + tlo - 1];
@@ -531,7 +542,7 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pb + tlo) : reinterpret_cast<const double*>(st.Pa);   // p1 of tlo / zero guard
 #pragma unroll
       for (int k = 0; k < ND; k++) {
-        const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
+        const double Wq = st.Gd[k * GP_GPD + dhi] - st.Gd[k * GP_GPD + dlo];
         sd[0][k] = (Wq - lo0_p[k * NT * 2]) + ev[(k * NT + thi) * 2];
         sd[1][k] = (Wq - ev[(k * NT + tlo) * 2]) + od[(k * NT + thi) * 2];
       }
@@ -544,7 +555,7 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
       const double* lo0_p = h ? reinterpret_cast<const double*>(st.Pa + tlo) + 1 : reinterpret_cast<const double*>(st.Pa);
 #pragma unroll
       for (int k = 0; k < ND; k++) {
-        const double Wq = st.Gd[k * GP + thi - 1] - st.Gd[k * GP + tlo - 1];
+        const double Wq = st.Gd[k * GP_GPD + dhi] - st.Gd[k * GP_GPD + dlo];
         const double2 b = hi_p[k * NT];
         sd[0][k] = (Wq - lo0_p[k * NT * 2]) + b.x;
         sd[1][k] = (Wq - lo1_p[k * NT * 2]) + b.y;
@@ -572,7 +583,7 @@ __device__ __forceinline__ void gp_window_pair(const GpStage& st, const GpGeo& g
         constexpr bool EO = GP_EVEN_ODD(ND);
         double pl = (el < 0) ? 0.0 : (((EO ? (el & 1) : (el >> 1)) ? Pb : Pa)[(k * NT + (zl >> 2)) * 2 + (EO ? (el >> 1) : (el & 1))]);
         double ph = (eh < 0) ? 0.0 : (((EO ? (eh & 1) : (eh >> 1)) ? Pb : Pa)[(k * NT + (zh >> 2)) * 2 + (EO ? (eh >> 1) : (eh & 1))]);
-        sd[cc][k] = (st.Gd[k * GP + (zh >> 2) - 1] + ph) - (st.Gd[k * GP + (zl >> 2) - 1] + pl);
+        sd[cc][k] = (st.Gd[k * GP_GPD + gp_dpos((zh >> 2) - 1)] + ph) - (st.Gd[k * GP_GPD + gp_dpos((zl >> 2) - 1)] + pl);
       }
     }
   }
@@ -677,7 +688,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gp_kernel(GfCommon gc, GfGeom g
 #pragma unroll
       for (int k = 0; k < P::NI; k++) st.Gi[k * GP_GP + i] = 0u;
 #pragma unroll
-      for (int k = 0; k < P::ND; k++) st.Gd[k * GP_GP + i] = 0.0;
+      for (int k = 0; k < P::ND; k++) st.Gd[k * GP_GPD + i] = 0.0;
+    }
+    for (int i = GP_GP + t; i < GP_GPD; i += GP_THREADS) {
+#pragma unroll
+      for (int k = 0; k < P::ND; k++) st.Gd[k * GP_GPD + i] = 0.0;
     }
   }
   if (t == 0) {
