@@ -307,6 +307,30 @@ def test_chain_batch_matches_single_and_device_path(ctx):
     assert (ctx.last_frame_flags(n) == 0).all()
 
 
+def test_chain_host_schedule(ctx, monkeypatch):
+    """uwip_chain_bgr8 cuts the batch into sub-batches (csrc/e2e_schedule.h; UWIP_E2E_SIZES replaces the schedule): whatever
+    the cut, the bytes are those of the device-resident call, and the per-frame flags line up with the frames."""
+    import torch
+
+    W, H, n = 160, 120, 12
+    frames = np.stack([O.synth_frame(0x5EED0004, i, W, H) for i in range(n)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.empty_like(d_in)
+    ctx.chain_dev(d_in, d_out, n, W, H)
+    ctx.synchronize()
+    want = d_out.cpu().numpy()
+    want_flags = np.asarray(ctx.last_frame_flags(n)).copy()
+    for sizes in (None, "1,2,4,3,2", "6,6", "2,6,4", "1,1,1,1,1,1,1,1,1,1,1,1", "3,3", "12"):   # the last two are ignored: "3,3" does not add up, "12" is one sub-batch (no copy could overlap)
+        if sizes is None:
+            monkeypatch.delenv("UWIP_E2E_SIZES", raising=False)
+        else:
+            monkeypatch.setenv("UWIP_E2E_SIZES", sizes)
+        got = ctx.chain(frames)
+        assert (got == want).all(), sizes
+        assert (np.asarray(ctx.last_frame_flags(n)) == want_flags).all(), sizes
+    monkeypatch.delenv("UWIP_E2E_SIZES", raising=False)
+
+
 def test_chain_nan_frame_matches_reference(ctx):
     """D9: where Yi = Yj = 0 the reference's S is 0/0 and the whole frame turns NaN (imwrite stores zeros).
     The CUDA path must flag exactly the frames the oracle does."""
