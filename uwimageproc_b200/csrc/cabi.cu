@@ -570,7 +570,7 @@ static int32_t* flags_get(uwip_ctx* ctx, int n) {
   return f;
 }
 
-// sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 512 KB table); keep it below 80 GB of the 180 GB
+// sub-batch size: the dehaze workspace is 60 B/px/frame (+ a 256 KB table; budgeted as 512 KB); keep it below 80 GB of the 180 GB
 // (UWIP_WORKSPACE_GB overrides) and below 70 % of what the device has free plus what this context already holds, and among
 // the sizes that fit take the one that wastes the fewest CTA waves of the marches (dehaze_sub_batch)
 static int sub_batch(const uwip_ctx* ctx, int n, int w, int h) {

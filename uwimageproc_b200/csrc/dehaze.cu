@@ -9,7 +9,7 @@
 //   -> GF1a: box sums of 17 moments + per-pixel 3x3 solve -> a,b planes (f32 x8)
 //   -> GF1b: box(a,b) -> refined t (D3,D5) -> J (D6) + min/max/sum reductions -> J planes (f32 x2)
 //   -> E: restored -> R8/I8 -> YCrCb joint min/max (D7,D8 first half); packed plane ycc = (Yi,Cri,Cbi,Yj)
-//   -> S table (256x256 f64 per frame: the exposure ratio is a function of two bytes)
+//   -> S table (256x256 u32 per frame: the exposure ratio is a function of two bytes; rint(S 2^28))
 //   -> GF2a: S + 13 moments + solve -> a,b (f32 x4)   -> GF2b: box(a,b) -> refined S, exposure min/max
 //   -> final: normalise, x255, rint, saturate -> bgr8 (D8 second half, D10)
 //
