@@ -207,7 +207,10 @@ void uwip_chain_defaults(uwip_chain_params* p);
 /* device resident: n_frames contiguous bgr8 frames in, same out (d_src may equal d_dst). */
 int uwip_chain_bgr8_dev(uwip_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int n_frames,
                         int width, int height, const uwip_chain_params* p);
-/* host buffers (pinned memory recommended): H2D, chain, D2H, double buffered in sub-batches. */
+/* host buffers (pinned memory recommended): H2D, chain, D2H pipelined over sub-batches through two staging buffers per
+ * direction; the sub-batch sizes ramp up and down in whole CTA waves (csrc/e2e_schedule.h) so that only a few frames'
+ * upload and download are exposed.  The bytes are those of the device-resident call whatever the schedule.  Returns after
+ * the last download has completed. */
 int uwip_chain_bgr8(uwip_ctx* ctx, const uint8_t* src, uint8_t* dst, int n_frames, int width,
                     int height, const uwip_chain_params* p);
 
